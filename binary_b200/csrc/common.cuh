@@ -1,0 +1,103 @@
+// Shared host/device helpers for libbinary_cuda (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/binary_cuda.h"
+
+namespace bcu {
+
+// ---- error plumbing: thread-local message behind bcu_last_error() ---------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+#define BCU_CUDA(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      ::bcu::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return (_e == cudaErrorMemoryAllocation) ? BCU_E_NOMEM : BCU_E_CUDA;                  \
+    }                                                                                       \
+  } while (0)
+
+#define BCU_TRY(expr)       \
+  do {                      \
+    int _s = (expr);        \
+    if (_s != BCU_OK) return _s; \
+  } while (0)
+
+#define BCU_LAUNCHED()                                  \
+  do {                                                  \
+    ::bcu::g_launches.fetch_add(1, std::memory_order_relaxed); \
+    BCU_CUDA(cudaGetLastError());                       \
+  } while (0)
+
+// RAII guard: make `device` current for the scope, restore on exit.
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != device && cudaSetDevice(device) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// ---- index layout in HBM --------------------------------------------------------------------------
+// One descriptor per distinct group value (sorted by gval). Rows [row_begin,row_end) of the sorted
+// arrays belong to the group; its directory slice is dir[bin_base .. bin_base+nb] (nb+1 entries).
+struct GroupDesc {
+  uint32_t gval;
+  uint32_t row_begin;
+  uint32_t row_end;
+  uint32_t nb;  // number of bins = (cmax >> shift) + 1, cmax = max coordinate (low or high) in group
+  uint64_t bin_base;
+};
+
+constexpr int kMaxSmemGroups = 256;
+
+}  // namespace bcu
+
+struct bcu_index {
+  int device = 0;
+  uint64_t n = 0;
+  uint32_t n_groups = 0;
+  uint32_t shift = 0;
+  uint32_t sort_passes = 0;
+  uint64_t n_bins = 0;
+  uint64_t bytes = 0;
+  uint2* d_lowhigh = nullptr;        // [n]   {low, high} of the targets sorted by (group, low, id)
+  uint32_t* d_id = nullptr;          // [n]   insertion ordinal of each sorted row
+  uint32_t* d_runmax = nullptr;      // [n]   running max of high inside the group (max-end array)
+  bcu::GroupDesc* d_groups = nullptr;  // [n_groups]
+  uint2* d_dir = nullptr;            // [n_bins] {lb, ub}: first row with runmax >= b*W / low >= b*W
+};
+
+namespace bcu {
+
+// K1: stable LSD radix sort of (key64, val32) pairs on `stream`; on return *out_keys/*out_vals point at
+// whichever of the two buffers holds the result. Only the digits in which the keys differ are run.
+int radix_sort_pairs(uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, uint64_t n,
+                     uint64_t varying_bits, cudaStream_t stream, uint64_t** out_keys,
+                     uint32_t** out_vals, uint32_t* passes);
+
+// Generic decoupled look-back scans (scan.cu)
+int exclusive_sum_u32(const uint32_t* d_in, uint32_t* d_out, uint64_t n, cudaStream_t stream);
+int segmented_running_max(const uint64_t* d_keys /* group in the high 32 bits */, const uint32_t* d_val,
+                          uint32_t* d_out, uint64_t n, cudaStream_t stream);
+
+// K3/K4 (join.cu)
+enum JoinMode { kModeCount = 0, kModeScatter = 1, kModeFused = 2, kModeAny = 3 };
+int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_qgroup,
+                const uint32_t* d_qlow, const uint32_t* d_qhigh, uint64_t* d_offsets,
+                uint64_t pair_capacity, uint32_t* d_hit_query, uint32_t* d_hit_target,
+                uint64_t* d_total, uint8_t* d_any, uint32_t query_id_base, cudaStream_t stream);
+
+}  // namespace bcu

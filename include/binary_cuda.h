@@ -1,0 +1,132 @@
+/* libbinary_cuda -- C ABI of the B200-native interval-overlap join.
+ *
+ * This is the one process/device boundary of the port. The reference (ylab-hi/BINARY) has NO FFI on
+ * this path: its boundary is the C++ class template binary::algorithm::tree::IntervalTree. Each
+ * entry point below names the reference interface it stands in for (paths relative to the
+ * reference checkout, library/include/binary/algorithm/...):
+ *
+ *   bcu_index_build*      <- RbTree::insert_node(R&&) / insert_node(Args&&...)   rb_tree.hpp:111-117,145-149
+ *                            + IntervalTree::insert_node_impl                   interval_tree.hpp:230-260
+ *                            (one tree per chromosome: sv2nl mapper.hpp:147-162 -> `group`)
+ *   bcu_query_count*      <- IntervalTree::find_overlaps(...).size()             interval_tree.hpp:161-168
+ *   bcu_query_scatter*    <- IntervalTree::find_overlaps / find_overlaps_impl    interval_tree.hpp:306-334
+ *   bcu_join*             <- the sv2nl hot loop: one find_overlaps per record    sv2nl mapper.hpp:207-218
+ *   bcu_query_any*        <- IntervalTree::find_overlap(...).has_value()         interval_tree.hpp:290-304
+ *   bcu_index_size        <- RbTree::size()                                      rb_tree.hpp:173-180
+ *
+ * Semantics (bit-exact with the reference): for query q and the multiset T of
+ * inserted intervals, the hits are { i : group(q)==group(T[i]) && q.low <= T[i].high &&
+ * T[i].low <= q.high } -- CLOSED intervals, evaluated exactly as written (interval_tree.hpp:119-121),
+ * so inverted intervals (low > high; TraMapper inserts such, sv2nl mapper.cpp:127-142) are neither
+ * rejected nor "fixed". Duplicates are distinct hits. target_id = 0-based insertion ordinal,
+ * query_id = 0-based position in the batch. Output is CSR: offsets[n_q+1] (u64) + pairs sorted by
+ * query_id; the order of targets inside one query is unspecified (the reference's is tree-shape
+ * preorder) -- the parity contract is the sorted set of (query_id, target_id) pairs.
+ *
+ * Conventions: every function returns 0 (BCU_OK) or a negative bcu_status; the message of the last
+ * failure on the calling thread is bcu_last_error(). No C++ types or exceptions cross the boundary.
+ * Host-pointer functions: the caller owns all host buffers (any memory; pinned memory from
+ * bcu_host_alloc is fastest), the library owns all device memory. `_dev` functions take DEVICE
+ * pointers on the index's device plus a cudaStream_t (passed as void*; NULL = default stream), are
+ * asynchronous with respect to the host and allocate scratch from the stream-ordered pool. An index
+ * is immutable after build and may be queried concurrently from several host threads/streams.
+ * There is no CPU fallback: without a usable CUDA device every call fails with BCU_E_CUDA.
+ */
+#ifndef BINARY_CUDA_H_
+#define BINARY_CUDA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum bcu_status {
+  BCU_OK = 0,
+  BCU_E_INVALID = -1,  /* bad argument                                              */
+  BCU_E_CUDA = -2,     /* CUDA runtime/driver error (message has the CUDA string)   */
+  BCU_E_NOMEM = -3,    /* host or device allocation failed                          */
+  BCU_E_CAPACITY = -4, /* caller-provided pair buffer too small; *total = required  */
+  BCU_E_LIMIT = -5     /* input exceeds a documented limit (n_t, n_q <= 2^32 - 2)   */
+} bcu_status;
+
+typedef struct bcu_index bcu_index; /* opaque; lives on one device */
+
+typedef struct bcu_index_info {
+  uint64_t n_targets;
+  uint32_t n_groups;     /* distinct group values among the targets                         */
+  uint32_t n_components; /* sub-lists of the AIList-style decomposition (1 = plain list)     */
+  uint32_t bin_shift;    /* directory bin width = 1 << bin_shift coordinate units            */
+  uint32_t sort_passes;  /* radix passes the build ran                                       */
+  uint64_t n_bins;       /* directory entries over all groups/components                     */
+  uint64_t device_bytes; /* device memory held by the index                                  */
+  int32_t device;
+  int32_t reserved;
+} bcu_index_info;
+
+/* ---- library / device ------------------------------------------------------------------------- */
+const char* bcu_version(void);
+const char* bcu_last_error(void);
+int bcu_device_count(int* n);
+
+/* Pinned host memory (cudaHostAlloc); optional, for fast host<->device copies. */
+int bcu_host_alloc(void** ptr, size_t bytes);
+int bcu_host_free(void* ptr);
+
+/* ---- build: K1 radix sort by (group, low) + K2 flat augmented index ----------------------------
+ * group may be NULL (= one group, id 0). Arrays are SoA u32, length n_t; target id = position. */
+int bcu_index_build(int device, uint64_t n_t, const uint32_t* group, const uint32_t* low,
+                    const uint32_t* high, bcu_index** out);
+int bcu_index_build_dev(int device, uint64_t n_t, const uint32_t* d_group, const uint32_t* d_low,
+                        const uint32_t* d_high, void* stream, bcu_index** out);
+int bcu_index_free(bcu_index* index);
+int bcu_index_size(const bcu_index* index, uint64_t* n_t);
+int bcu_index_get_info(const bcu_index* index, bcu_index_info* info);
+
+/* ---- query, host buffers (H2D/D2H inside the call) ----------------------------------------------
+ * qgroup may be NULL (= group 0). offsets has n_q+1 entries. */
+int bcu_query_count(const bcu_index* index, uint64_t n_q, const uint32_t* qgroup,
+                    const uint32_t* qlow, const uint32_t* qhigh, uint64_t* offsets,
+                    uint64_t* total);
+int bcu_query_scatter(const bcu_index* index, uint64_t n_q, const uint32_t* qgroup,
+                      const uint32_t* qlow, const uint32_t* qhigh, const uint64_t* offsets,
+                      uint32_t* hit_query, uint32_t* hit_target);
+/* One call, one pass over the queries: count, prefix-sum and scatter fused in one kernel, chunks
+ * pipelined over copy/compute streams. pair_capacity = entries available in hit_query/hit_target;
+ * if the join produces more, returns BCU_E_CAPACITY with *total = required entries (offsets are
+ * complete and valid in that case, pairs are not). */
+int bcu_join(const bcu_index* index, uint64_t n_q, const uint32_t* qgroup, const uint32_t* qlow,
+             const uint32_t* qhigh, uint64_t* offsets, uint64_t pair_capacity, uint32_t* hit_query,
+             uint32_t* hit_target, uint64_t* total);
+/* any[i] = 1 iff query i overlaps at least one target (shape-independent part of find_overlap). */
+int bcu_query_any(const bcu_index* index, uint64_t n_q, const uint32_t* qgroup,
+                  const uint32_t* qlow, const uint32_t* qhigh, uint8_t* any);
+
+/* ---- query, device buffers (no PCIe; what the roofline is measured on) --------------------------
+ * d_offsets: u64[n_q+1] exclusive prefix sums, d_offsets[n_q] = total. */
+int bcu_query_count_dev(const bcu_index* index, uint64_t n_q, const uint32_t* d_qgroup,
+                        const uint32_t* d_qlow, const uint32_t* d_qhigh, uint64_t* d_offsets,
+                        void* stream);
+int bcu_query_scatter_dev(const bcu_index* index, uint64_t n_q, const uint32_t* d_qgroup,
+                          const uint32_t* d_qlow, const uint32_t* d_qhigh,
+                          const uint64_t* d_offsets, uint32_t* d_hit_query, uint32_t* d_hit_target,
+                          void* stream);
+/* Fused single pass. d_total: u64[1] on device, receives the number of pairs the join has (also
+ * when it exceeds pair_capacity, in which case pairs beyond the capacity are not written).
+ * query_id_base is added to every emitted query id, offset_base to every offset (for sharding). */
+int bcu_join_dev(const bcu_index* index, uint64_t n_q, const uint32_t* d_qgroup,
+                 const uint32_t* d_qlow, const uint32_t* d_qhigh, uint64_t* d_offsets,
+                 uint64_t pair_capacity, uint32_t* d_hit_query, uint32_t* d_hit_target,
+                 uint64_t* d_total, uint32_t query_id_base, void* stream);
+int bcu_query_any_dev(const bcu_index* index, uint64_t n_q, const uint32_t* d_qgroup,
+                      const uint32_t* d_qlow, const uint32_t* d_qhigh, uint8_t* d_any,
+                      void* stream);
+
+/* Number of kernel launches this library has issued on the calling process (all threads). */
+uint64_t bcu_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BINARY_CUDA_H_ */

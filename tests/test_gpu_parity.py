@@ -1,0 +1,188 @@
+"""GPU (-m gpu): the CUDA path through the C ABI vs the oracle, bit-exact as the sorted set of
+(query_id, target_id) pairs. Integer work: no tolerance anywhere."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from binary_b200 import DeviceIndex, IntervalTree, synth
+from cases import CLRS_NODES, canonical, clrs_arrays, random_case
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _check_all_entry_points(c, port):
+    """count / scatter / fused join / any, all against the oracle tree walk."""
+    f = port.build(c["tl"], c["th"], c["tg"])
+    want_off, want_tid = f.query_sorted_pairs(c["ql"], c["qh"], c["qg"], threads=4)
+    ix = DeviceIndex.build(c["tl"], c["th"], c["tg"])
+    assert len(ix) == c["tl"].size
+    # two-call ABI
+    off = ix.count(c["ql"], c["qh"], c["qg"])
+    assert np.array_equal(off, want_off)
+    hq, ht = ix.scatter(c["ql"], c["qh"], off, c["qg"])
+    counts = np.diff(want_off).astype(np.int64)
+    want_q = np.repeat(np.arange(counts.size, dtype=np.uint32), counts)
+    assert np.array_equal(hq, want_q)
+    assert np.array_equal(canonical(off, ht)[1], want_tid)
+    # fused single pass
+    off2, hq2, ht2 = ix.join(c["ql"], c["qh"], c["qg"])
+    assert np.array_equal(off2, want_off) and np.array_equal(hq2, want_q)
+    assert np.array_equal(canonical(off2, ht2)[1], want_tid)
+    # any-overlap bit (shape-independent part of find_overlap)
+    assert np.array_equal(ix.any(c["ql"], c["qh"], c["qg"]), counts > 0)
+    ix.close()
+    return int(want_off[-1])
+
+
+def test_reference_known_answers_through_the_drop_in_api():
+    # test_interval_tree.cpp:87-137,146-155 re-expressed against the GPU path
+    t = IntervalTree()
+    t.insert_node(CLRS_NODES)
+    assert t.size() == 10 and not t.empty()
+    assert len(t.find_overlaps(7, 25)) == 8
+    assert len(t.find_overlaps(15, 25)) == 5
+    assert {(a, b) for a, b, _ in t.find_overlaps(15, 25)} == {(16, 21), (15, 23), (19, 20), (17, 19), (25, 30)}
+    assert t.find_overlap(22, 25)[:2] == (15, 23)   # the only overlapping interval
+    assert t.find_overlap(100, 111) is None
+    d = IntervalTree()
+    for _ in range(4):
+        d.insert_node(1, 4)
+    assert d.size() == 4 and len(d.find_overlaps(2, 5)) == 4
+    s = IntervalTree()
+    lo = np.arange(0, 1000, 2, dtype=np.uint32)
+    s.insert_node(lo, lo + 3)
+    assert s.size() == 500
+    assert len(s.find_overlaps(10, 10)) == 2
+
+
+def test_golden_fixtures_from_reference():
+    for name in sorted(os.listdir(GOLDEN)):
+        if not (name.startswith("ref_") and name.endswith(".json")):
+            continue
+        g = json.load(open(os.path.join(GOLDEN, name)))
+        arr = lambda k: None if g[k] is None else np.array(g[k], np.uint32)
+        ix = DeviceIndex.build(arr("tl"), arr("th"), arr("tg"))
+        off, hq, ht = ix.join(arr("ql"), arr("qh"), arr("qg"))
+        want_off = np.array(g["offsets"], np.uint64)
+        assert np.array_equal(off, want_off), name
+        assert np.array_equal(canonical(off, ht)[1], canonical(want_off, np.array(g["targets_native"], np.uint32))[1]), name
+
+
+@pytest.mark.parametrize("seed,kw", [
+    (1, dict(n_t=5000, n_q=3000)),
+    (2, dict(n_t=5000, n_q=3000, n_groups=5, q_groups=7)),
+    (3, dict(n_t=4000, n_q=2500, inverted_frac=0.3, dup_frac=0.2, extremes=True)),
+    (4, dict(n_t=4000, n_q=2500, long_frac=0.02, n_groups=3)),
+    (5, dict(n_t=1, n_q=1)),
+    (6, dict(n_t=3, n_q=1025, span=50, max_len=10)),
+    (7, dict(n_t=2049, n_q=7, span=100, max_len=100)),          # every query hits ~everything
+    (8, dict(n_t=60000, n_q=40000, span=4_000_000_000, max_len=100000, n_groups=300, q_groups=310)),
+    (9, dict(n_t=20000, n_q=5000, span=200000, max_len=60000)),  # dense: warp-cooperative path
+])
+def test_random_cases_all_entry_points(port_oracle, seed, kw):
+    _check_all_entry_points(random_case(seed, **kw), port_oracle)
+
+
+def test_empty_inputs(port_oracle):
+    e = np.empty(0, np.uint32)
+    ix = DeviceIndex.build(e, e)
+    assert len(ix) == 0
+    off, hq, ht = ix.join(np.array([1, 2], np.uint32), np.array([3, 4], np.uint32))
+    assert list(off) == [0, 0, 0] and hq.size == 0 and ht.size == 0
+    assert list(ix.count([5], [9])) == [0, 0]
+    ix2 = DeviceIndex.build(np.array([1], np.uint32), np.array([2], np.uint32))
+    off, hq, ht = ix2.join(e, e)
+    assert list(off) == [0] and hq.size == 0
+    assert ix2.any(e, e).size == 0
+
+
+def test_pair_capacity_is_reported():
+    from binary_b200 import _lib
+    import ctypes as C
+    lo = np.zeros(100, np.uint32)
+    hi = np.full(100, 10, np.uint32)
+    ix = DeviceIndex.build(lo, hi)
+    ql = np.zeros(10, np.uint32)
+    off = np.empty(11, np.uint64)
+    hq = np.empty(5, np.uint32)
+    ht = np.empty(5, np.uint32)
+    total = C.c_uint64()
+    rc = _lib.load().bcu_join(ix._h, 10, None, ql.ctypes.data, ql.ctypes.data, off.ctypes.data, 5,
+                              hq.ctypes.data, ht.ctypes.data, C.byref(total))
+    assert rc == _lib.BCU_E_CAPACITY and total.value == 1000
+    assert list(off) == [100 * i for i in range(11)]
+    off2, hq2, ht2 = ix.join(ql, ql, pair_capacity=5)   # wrapper grows and retries
+    assert hq2.size == 1000
+
+
+@pytest.mark.parametrize("name,n_t,n_q", [("B", 200_000, 100_000), ("C", 200_000, 20_000), ("D", 400_000, 100_000)])
+def test_baseline_configs_scaled_vs_tree_oracle(port_oracle, name, n_t, n_q):
+    """BASELINE.json configs 2-4 at oracle-friendly sizes, same laws/seeds as the bench."""
+    w = synth.CONFIGS[name].scaled(n_t, n_q)
+    tg, tl, th = w.targets()
+    qg, ql, qh = w.queries()
+    hits = _check_all_entry_points(dict(tl=tl, th=th, tg=tg, ql=ql, qh=qh, qg=qg), port_oracle)
+    assert hits > 0
+
+
+def test_against_unmodified_reference(ref_oracle):
+    """Where the prebuilt reference travels with the repo: GPU vs the reference headers themselves."""
+    c = random_case(31, n_t=30000, n_q=20000, n_groups=6, inverted_frac=0.05, dup_frac=0.05, extremes=True,
+                    long_frac=0.002)
+    f = ref_oracle.build(c["tl"], c["th"], c["tg"])
+    want_off, want_tid = f.query_sorted_pairs(c["ql"], c["qh"], c["qg"], threads=4)
+    ix = DeviceIndex.build(c["tl"], c["th"], c["tg"])
+    off, hq, ht = ix.join(c["ql"], c["qh"], c["qg"])
+    assert np.array_equal(off, want_off)
+    assert np.array_equal(canonical(off, ht)[1], want_tid)
+
+
+@pytest.mark.parametrize("name", ["B", "C"])
+def test_full_size_configs_count_and_hash(port_oracle, name):
+    """BASELINE.json's full sizes (1M x 10M): total hit count, per-query counts and an order-independent
+    64-bit hash of all pairs vs the CPU flat-index twin (itself proven equal to the tree walk)."""
+    import torch
+    w = synth.CONFIGS[name]
+    n_q = w.n_queries if name == "B" else 2_000_000   # C at 10M is 6.6 GB of pairs; 2M keeps CPU time sane
+    tg, tl, th = w.targets()
+    qg, ql, qh = w.queries(0, n_q)
+    want_total, want_hash, want_counts = port_oracle.flat_count_hash(tl, th, ql, qh, tg, qg, want_counts=True)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(a.view(np.int32)).to(dev)
+    d_tg, d_tl, d_th, d_qg, d_ql, d_qh = map(t, (tg, tl, th, qg, ql, qh))
+    ix = DeviceIndex.build_dev(tl.size, d_tl.data_ptr(), d_th.data_ptr(), d_tg.data_ptr())
+    d_off = torch.empty(n_q + 1, dtype=torch.int64, device=dev)
+    cap = want_total + 16
+    d_hq = torch.empty(cap, dtype=torch.int32, device=dev)
+    d_ht = torch.empty(cap, dtype=torch.int32, device=dev)
+    d_total = torch.zeros(1, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    ix.join_dev(n_q, d_ql.data_ptr(), d_qh.data_ptr(), d_off.data_ptr(), cap, d_hq.data_ptr(), d_ht.data_ptr(),
+                d_total.data_ptr(), d_qg.data_ptr(), 0, stream)
+    torch.cuda.synchronize()
+    assert int(d_total.item()) == want_total
+    off = d_off.cpu().numpy().view(np.uint64)
+    assert np.array_equal(np.diff(off), want_counts)
+    hq = d_hq[:want_total].cpu().numpy().view(np.uint32)
+    ht = d_ht[:want_total].cpu().numpy().view(np.uint32)
+    assert port_oracle.pair_hash(hq, ht) == want_hash
+    # two-call path on the same data: count == fused offsets; scatter == same pair multiset
+    d_off2 = torch.empty_like(d_off)
+    ix.count_dev(n_q, d_ql.data_ptr(), d_qh.data_ptr(), d_off2.data_ptr(), d_qg.data_ptr(), stream)
+    d_hq.zero_(); d_ht.zero_()
+    ix.scatter_dev(n_q, d_ql.data_ptr(), d_qh.data_ptr(), d_off2.data_ptr(), d_hq.data_ptr(), d_ht.data_ptr(),
+                   d_qg.data_ptr(), stream)
+    torch.cuda.synchronize()
+    assert torch.equal(d_off, d_off2)
+    assert port_oracle.pair_hash(d_hq[:want_total].cpu().numpy().view(np.uint32),
+                                 d_ht[:want_total].cpu().numpy().view(np.uint32)) == want_hash
+    # size-independent property: queries are independent -> any prefix of the batch gives a prefix
+    half = n_q // 2
+    d_off3 = torch.empty(half + 1, dtype=torch.int64, device=dev)
+    ix.count_dev(half, d_ql.data_ptr(), d_qh.data_ptr(), d_off3.data_ptr(), d_qg.data_ptr(), stream)
+    torch.cuda.synchronize()
+    assert torch.equal(d_off3, d_off[: half + 1])
