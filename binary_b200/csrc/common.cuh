@@ -70,6 +70,7 @@ struct bcu_index {
   uint64_t n = 0;
   uint32_t n_groups = 0;
   uint32_t shift = 0;
+  uint32_t max_gval = 0;  // largest group value (selects the direct group map in join.cu)
   uint32_t sort_passes = 0;
   uint64_t n_bins = 0;
   uint64_t bytes = 0;

@@ -221,6 +221,7 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
     n_bins += (uint64_t)descs[g].nb + 1;
   }
   ix->n_groups = n_groups;
+  ix->max_gval = n_groups ? gval[n_groups - 1] : 0;
   ix->shift = shift;
   ix->n_bins = n_bins;
   BCU_CUDA(cudaMalloc((void**)&ix->d_groups, (size_t)n_groups * sizeof(GroupDesc)));
