@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbinary_cuda.so")
+LIB_PATH = os.environ.get("BINARY_B200_LIB") or os.path.join(_HERE, "libbinary_cuda.so")
 
 BCU_OK, BCU_E_INVALID, BCU_E_CUDA, BCU_E_NOMEM, BCU_E_CAPACITY, BCU_E_LIMIT = 0, -1, -2, -3, -4, -5
 

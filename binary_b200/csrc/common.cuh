@@ -52,12 +52,12 @@ struct DeviceGuard {
 
 // ---- index layout in HBM --------------------------------------------------------------------------
 // One descriptor per distinct group value (sorted by gval). Rows [row_begin,row_end) of the sorted
-// arrays belong to the group; its directory slice is dir[bin_base .. bin_base+nb] (nb+1 entries).
+// arrays belong to the group; its directory slice is dir[bin_base .. bin_base+nb).
 struct GroupDesc {
   uint32_t gval;
   uint32_t row_begin;
   uint32_t row_end;
-  uint32_t nb;  // number of bins = (cmax >> shift) + 1, cmax = max coordinate (low or high) in group
+  uint32_t nb;  // number of bins = directory entries = (cmax >> shift) + 1, cmax = max coordinate in group
   uint64_t bin_base;
 };
 
@@ -74,11 +74,11 @@ struct bcu_index {
   uint32_t sort_passes = 0;
   uint64_t n_bins = 0;
   uint64_t bytes = 0;
-  uint2* d_lowhigh = nullptr;        // [n]   {low, high} of the targets sorted by (group, low, id)
+  uint2* d_lowhigh = nullptr;        // [n+2] {low, high} of the targets sorted by (group, low, id)
   uint32_t* d_id = nullptr;          // [n]   insertion ordinal of each sorted row
   uint32_t* d_runmax = nullptr;      // [n]   running max of high inside the group (max-end array)
   bcu::GroupDesc* d_groups = nullptr;  // [n_groups]
-  uint2* d_dir = nullptr;            // [n_bins] {lb, ub}: first row with runmax >= b*W / low >= b*W
+  uint2* d_dir = nullptr;            // [n_bins] entry b = {first row with runmax >= b*W, first row with low >= (b+1)*W}
 };
 
 namespace bcu {

@@ -6,10 +6,11 @@
 //   rows sorted by (group, low, id)            <- K1 (radix_sort.cu), stable so ties keep id order
 //   lowhigh[r] = {low, high}, id[r]            <- gather
 //   runmax[r]  = max(high[group_begin..r])     <- segmented running max (scan.cu), the "max-end" array
-//   dir[g][b]  = { first row with runmax >= b*W , first row with low >= b*W },  W = 1 << shift
+//   dir[g][b]  = { first row with runmax >= b*W , first row with low >= (b+1)*W },  W = 1 << shift
 // The directory turns both searches of a query (upper bound of q.high in `low`, lower bound of q.low in
-// `runmax`) into one 8-byte load each; the few rows of slack it admits are rejected by the exact
-// predicate in the scan (join.cu), so results do not depend on W.
+// `runmax`) into ONE 8-byte load when the query lies inside one bin (two otherwise); the few rows of
+// slack it admits are rejected by the exact predicate in the scan (join.cu), so results do not depend
+// on W.
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
@@ -88,20 +89,20 @@ __global__ void __launch_bounds__(kThreads)
     if (groups[mid].bin_base <= e) lo = mid; else hi = mid;
   }
   const GroupDesc g = groups[lo];
-  const uint64_t thr = (e - g.bin_base) << shift;  // b * W, may exceed 32 bits for the sentinel entry
-  uint32_t lb = g.row_end, ub = g.row_end;
-  if (thr <= 0xffffffffull) {
-    const uint32_t t = (uint32_t)thr;
-    uint32_t a = g.row_begin, b = g.row_end;
-    while (a < b) {  // first row with runmax >= t
-      uint32_t m = a + ((b - a) >> 1);
-      if (runmax[m] < t) a = m + 1; else b = m;
-    }
-    lb = a;
+  const uint64_t t0 = (e - g.bin_base) << shift;  // b * W       (<= cmax, fits 32 bits)
+  const uint64_t t1 = t0 + (1ull << shift);       // (b + 1) * W (may exceed 32 bits in the last bin)
+  uint32_t a = g.row_begin, b = g.row_end;
+  while (a < b) {  // first row with runmax >= b*W
+    uint32_t m = a + ((b - a) >> 1);
+    if (runmax[m] < (uint32_t)t0) a = m + 1; else b = m;
+  }
+  const uint32_t lb = a;
+  uint32_t ub = g.row_end;
+  if (t1 <= 0xffffffffull) {
     a = g.row_begin; b = g.row_end;
-    while (a < b) {  // first row with low >= t
+    while (a < b) {  // first row with low >= (b+1)*W
       uint32_t m = a + ((b - a) >> 1);
-      if (lowhigh[m].x < t) a = m + 1; else b = m;
+      if (lowhigh[m].x < (uint32_t)t1) a = m + 1; else b = m;
     }
     ub = a;
   }
@@ -140,9 +141,24 @@ struct TempBuffers {  // freed on every exit path
   }
 };
 
+// Keep stream-ordered scratch cached in the device pool (the default threshold of 0 hands it back to
+// the driver at every synchronisation, which costs milliseconds per call).
+static void keep_pool_warm(int device) {
+  static std::atomic<unsigned long long> done{0};
+  if (device < 0 || device >= 64 || (done.load() >> device) & 1ull) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t threshold = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+  }
+  cudaGetLastError();
+  done.fetch_or(1ull << device);
+}
+
 static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, const uint32_t* d_low,
                            const uint32_t* d_high, cudaStream_t stream) {
   ix->n = n;
+  keep_pool_warm(ix->device);
   if (n == 0) return BCU_OK;
   TempBuffers tmp(stream);
   uint64_t *keys_a, *keys_b;
@@ -169,7 +185,8 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
   BCU_TRY(radix_sort_pairs(keys_a, keys_b, vals_a, vals_b, n, varying, stream, &keys, &vals,
                            &ix->sort_passes));
 
-  BCU_CUDA(cudaMalloc((void**)&ix->d_lowhigh, n * sizeof(uint2)));
+  BCU_CUDA(cudaMalloc((void**)&ix->d_lowhigh, (n + 2) * sizeof(uint2)));  // +pad: join.cu reads row pairs
+  BCU_CUDA(cudaMemsetAsync(ix->d_lowhigh + n, 0, 2 * sizeof(uint2), stream));
   BCU_CUDA(cudaMalloc((void**)&ix->d_id, n * 4));
   BCU_CUDA(cudaMalloc((void**)&ix->d_runmax, n * 4));
   ix->bytes += n * 16;
@@ -200,13 +217,13 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
   BCU_CUDA(cudaStreamSynchronize(stream));
 
   // ---- bin width: smallest shift whose directory stays within ~bin_factor entries per target ----
-  const double factor = env_double("BCU_BIN_FACTOR", 1.0);
+  const double factor = env_double("BCU_BIN_FACTOR", 4.0);
   const uint64_t budget = std::max<uint64_t>((uint64_t)(factor * (double)n), 1024) + 2ull * n_groups;
   uint32_t shift = 0;
   uint64_t n_bins = 0;
   for (shift = 0; shift <= 31; ++shift) {
     n_bins = 0;
-    for (uint32_t g = 0; g < n_groups; ++g) n_bins += ((uint64_t)cmax[g] >> shift) + 2;
+    for (uint32_t g = 0; g < n_groups; ++g) n_bins += ((uint64_t)cmax[g] >> shift) + 1;
     if (n_bins <= budget) break;
   }
   if (shift > 31) shift = 31;
@@ -218,7 +235,7 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
     descs[g].row_end = (g + 1 < n_groups) ? heads[g + 1] : (uint32_t)n;
     descs[g].nb = (uint32_t)(((uint64_t)cmax[g] >> shift) + 1);
     descs[g].bin_base = n_bins;
-    n_bins += (uint64_t)descs[g].nb + 1;
+    n_bins += (uint64_t)descs[g].nb;
   }
   ix->n_groups = n_groups;
   ix->max_gval = n_groups ? gval[n_groups - 1] : 0;
@@ -245,7 +262,7 @@ extern "C" int bcu_index_build_dev(int device, uint64_t n_t, const uint32_t* d_g
                                    bcu_index** out) {
   if (!out) { set_error("bcu_index_build: out is NULL"); return BCU_E_INVALID; }
   *out = nullptr;
-  if (n_t > 0xfffffffeull) { set_error("bcu_index_build: n_t exceeds 2^32-2"); return BCU_E_LIMIT; }
+  if (n_t > 0x7fffffffull) { set_error("bcu_index_build: n_t exceeds 2^31-1"); return BCU_E_LIMIT; }
   if (n_t && (!d_low || !d_high)) { set_error("bcu_index_build: low/high are NULL"); return BCU_E_INVALID; }
   DeviceGuard guard(device);
   if (!guard.ok) { set_error("bcu_index_build: cannot select CUDA device %d", device); return BCU_E_CUDA; }
@@ -266,7 +283,7 @@ extern "C" int bcu_index_build(int device, uint64_t n_t, const uint32_t* group, 
                                const uint32_t* high, bcu_index** out) {
   if (!out) { set_error("bcu_index_build: out is NULL"); return BCU_E_INVALID; }
   *out = nullptr;
-  if (n_t > 0xfffffffeull) { set_error("bcu_index_build: n_t exceeds 2^32-2"); return BCU_E_LIMIT; }
+  if (n_t > 0x7fffffffull) { set_error("bcu_index_build: n_t exceeds 2^31-1"); return BCU_E_LIMIT; }
   if (n_t && (!low || !high)) { set_error("bcu_index_build: low/high are NULL"); return BCU_E_INVALID; }
   DeviceGuard guard(device);
   if (!guard.ok) { set_error("bcu_index_build: cannot select CUDA device %d", device); return BCU_E_CUDA; }

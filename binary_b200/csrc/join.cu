@@ -1,40 +1,48 @@
-// K3 + K4 -- the batched overlap join: per-query bound lookup, candidate scan, count -> prefix sum ->
-// scatter of (query_id, target_id) pairs.
+// K3 + K4 -- the batched overlap join: per-query bound lookup + candidate scan (K3), then
+// count -> prefix sum -> scatter of (query_id, target_id) pairs (K4).
 //
 // Reference being replaced: IntervalTree::find_overlaps / find_overlaps_impl
 // (interval_tree.hpp:161-168, 306-334), one recursive pruned walk + vector copies per query, driven
 // once per record by sv2nl (mapper.hpp:207-218).
 //
-// Execution model: a persistent grid (one wave of resident CTAs); every WARP owns a tile of 128
-// consecutive queries (4 per lane, one 128-bit load per input column) and loops over tiles
-// warp-stride. There is no block-level synchronisation in the loop: warps run fully decoupled, which
-// is what hides the three dependent L2 round trips of a query (directory -> candidate rows -> ids).
-//   1. bounds    lb = dir[bin(q.low)].lb, ub = dir[bin(q.high)+1].ub  (two 8-byte loads; the
-//                directory replaces both binary searches, index_build.cu)
-//   2. count     rows [lb,ub) are a superset of the hits; the exact predicate
-//                q.low <= t.high && t.low <= q.high (interval_tree.hpp:119-121) is evaluated on each.
-//                Short ranges: by the owning lane, the 4 queries of a lane interleaved so their loads
-//                overlap; the hit bitmask stays in a register.
-//                Long ranges: warp-cooperatively, 32 rows per step, __ballot_sync/__popc.
-//   3. prefix    warp scan of the counts + decoupled look-back across tiles (lookback.cuh): the u64 CSR
-//                offsets come out of the SAME kernel, in query order
-//   4. scatter   short ranges: hit rows are staged in shared memory at their tile-local rank, then the
-//                warp writes (query_id, target_id) to consecutive addresses; long ranges re-scan with
-//                ballot/popc compaction.
-// Modes: kModeFused = 1-4 in one launch; kModeCount = 1-3 (offsets only); kModeScatter = 1,2,4 with
-// offsets given (the two-call ABI); kModeAny = 1-2, writes (count > 0).
+// Two launches, no inter-CTA waiting anywhere (a single-pass chained scan was measured first: with
+// ~600 resident tiles of random-latency work every tile ends up waiting for the slowest in-flight
+// predecessor):
+//
+//   probe_kernel   K3. The query batch is cut into contiguous chunks, one per CTA; inside a chunk every
+//                  WARP takes 128 consecutive queries at a time (4 per lane, one 128-bit load per input
+//                  column) and never synchronises with other warps.
+//                    bounds: lb = dir[bin(q.low)].lb, ub = dir[bin(q.high)].ub -- ONE 8-byte load when the
+//                            query lies inside one directory bin (the directory replaces both binary
+//                            searches; index_build.cu)
+//                    count : rows [lb,ub) are a superset of the hits; the exact predicate
+//                            q.low <= t.high && t.low <= q.high (interval_tree.hpp:119-121) is evaluated
+//                            on each. Short ranges: by the owning lane, its 4 queries interleaved so
+//                            their loads overlap, result = a hit bitmask. Long ranges: by the whole warp,
+//                            128 rows per trip with 128-bit loads.
+//                  Output: per query 8 bytes of state {lb, hit mask | count} + one hit total per CTA.
+//   emit_kernel    K4. Same chunks. A CTA first sums the totals of the chunks before its own (its
+//                  global base), then walks its chunk 1024 queries at a time: counts from the state ->
+//                  warp scan + one barrier -> u64 CSR offsets, in query order; short-range hits are staged
+//                  in shared memory at their rank, gathered to target ids, and written to consecutive
+//                  addresses; long ranges are re-scanned by the warp with ballot/popc compaction.
+//
+//   direct_kernel  the two-call ABI's second half (offsets supplied by the caller) and the any-overlap
+//                  bit: bounds + scan + scatter without any prefix step.
 #include "common.cuh"
-#include "lookback.cuh"
 
 namespace bcu {
 
 constexpr int kJoinThreads = 256;
 constexpr int kJoinWarps = kJoinThreads / 32;
-constexpr int kQPT = 4;                  // queries per lane: one 128-bit load per input column
-constexpr int kWarpTile = 32 * kQPT;     // 128 queries per warp tile
-constexpr uint32_t kScalarMax = 16;      // longer candidate ranges go to the warp-cooperative path
-constexpr int kStage = 256;              // staged hits per warp and round
-constexpr int kDirectGroups = 1024;      // group values below this use a direct map
+constexpr int kQPT = 4;                            // queries per lane: one 128-bit load per input column
+constexpr int kWarpTile = 32 * kQPT;               // 128 queries per warp step
+constexpr int kCtaTile = kJoinWarps * kWarpTile;   // 1024 queries per CTA step
+constexpr int kJoinMinBlocks = 4;
+constexpr uint32_t kScalarMax = 16;                // longer candidate ranges go to the warp-cooperative path
+constexpr int kStage = 256;                        // staged hits per warp and round
+constexpr int kDirectGroups = 1024;                // group values below this use a direct map
+constexpr uint32_t kBigFlag = 0x80000000u;         // state word: bit 31 = long range, low bits = hit count
 
 struct JoinArgs {
   const uint2* __restrict__ lowhigh;
@@ -48,8 +56,8 @@ struct JoinArgs {
   const uint32_t* __restrict__ qlow;
   const uint32_t* __restrict__ qhigh;
   uint32_t n_q;
-  uint32_t n_tiles;
-  int vec_ok;  // all query columns (and offsets) are 16-byte aligned
+  uint32_t chunk;  // queries per CTA chunk (multiple of kCtaTile); direct_kernel: unused
+  int vec_ok;      // all query columns (and offsets) are 16-byte aligned
   uint64_t* offsets;
   uint64_t capacity;
   uint32_t* __restrict__ hit_query;
@@ -57,21 +65,63 @@ struct JoinArgs {
   uint64_t* total;
   uint8_t* __restrict__ any;
   uint32_t qid_base;
-  uint64_t* status;
+  uint32_t* st_lb;      // [n_q rounded up to kCtaTile] probe state: first candidate row
+  uint32_t* st_w;       // [same] probe state: hit bitmask, or kBigFlag | hit count
+  uint64_t* cta_total;  // [gridDim.x] hits per chunk
 };
 
-struct JoinSmem {
-  uint32_t g_val[kMaxSmemGroups];   // sorted group values (binary-search mode)
+struct GroupTables {
+  uint32_t g_val[kMaxSmemGroups];  // sorted group values (binary-search mode)
   uint32_t g_nb[kMaxSmemGroups];
   uint64_t g_base[kMaxSmemGroups];
-  uint16_t g_map[kDirectGroups];    // group value -> descriptor index, 0xffff = absent (direct mode)
-  uint64_t st_pos[kJoinWarps][kStage];
-  uint32_t st_row[kJoinWarps][kStage];
-  uint8_t st_qi[kJoinWarps][kStage];
+  uint16_t g_map[kDirectGroups];   // group value -> descriptor index, 0xffff = absent (direct mode)
 };
 
-__device__ __forceinline__ bool overlaps(uint32_t ql, uint32_t qh, uint2 t) {
-  return (ql <= t.y) & (t.x <= qh);
+struct StageBuffers {
+  uint64_t pos[kJoinWarps][kStage];  // output position of each staged hit (relative to the warp's base)
+  uint32_t val[kJoinWarps][kStage];  // sorted-row index of the hit
+  uint8_t qi[kJoinWarps][kStage];    // query index inside the warp's 128
+};
+
+// Read-only 128/64-bit loads as ONE instruction. Written as PTX because the compiler otherwise may split
+// a struct load whose fields are used under different predicates into dependent scalar loads.
+__device__ __forceinline__ uint4 ldg_u4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint2 ldg_u2(const uint2* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) {
+  return __shfl_sync(0xffffffffu, (unsigned long long)v, src);
+}
+
+__device__ __forceinline__ bool overlaps(uint32_t ql, uint32_t qh, uint32_t tl, uint32_t th) {
+  return (ql <= th) & (tl <= qh);
+}
+
+// group tables -> shared memory, once per CTA (ends with a barrier)
+__device__ __forceinline__ void load_group_tables(const JoinArgs& a, GroupTables& tb) {
+  const int tid = threadIdx.x;
+  const bool in_smem = a.n_groups <= (uint32_t)kMaxSmemGroups;
+  const bool direct = in_smem && a.max_gval < (uint32_t)kDirectGroups;
+  if (in_smem) {
+    if (direct)
+      for (int g = tid; g < kDirectGroups; g += kJoinThreads) tb.g_map[g] = 0xffffu;
+    __syncthreads();
+    for (uint32_t g = tid; g < a.n_groups; g += kJoinThreads) {
+      const GroupDesc d = a.groups[g];
+      tb.g_val[g] = d.gval;
+      tb.g_nb[g] = d.nb;
+      tb.g_base[g] = d.bin_base;
+      if (direct) tb.g_map[d.gval] = (uint16_t)g;
+    }
+  }
+  __syncthreads();
 }
 
 __device__ __forceinline__ void load_queries(const JoinArgs& a, uint32_t q0, uint32_t (&ql)[kQPT],
@@ -90,7 +140,7 @@ __device__ __forceinline__ void load_queries(const JoinArgs& a, uint32_t q0, uin
   } else {
 #pragma unroll
     for (int j = 0; j < kQPT; ++j) {
-      bool v = q0 + j < a.n_q;  // q0 may be past the end for the prefetch of a non-existent tile
+      bool v = q0 + j < a.n_q;  // q0 may be past the end when prefetching
       ql[j] = v ? a.qlow[q0 + j] : 0u;
       qh[j] = v ? a.qhigh[q0 + j] : 0u;
       qg[j] = (v && a.qgroup) ? a.qgroup[q0 + j] : 0u;
@@ -98,242 +148,387 @@ __device__ __forceinline__ void load_queries(const JoinArgs& a, uint32_t q0, uin
   }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kJoinThreads) join_kernel(const JoinArgs a) {
-  __shared__ JoinSmem sm;
-  constexpr bool kNeedsPrefix = (MODE == kModeCount || MODE == kModeFused);
-  constexpr bool kEmits = (MODE == kModeScatter || MODE == kModeFused);
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // ---- group tables -> shared memory, once per CTA --------------------------------------------------
-  const bool direct = a.max_gval < (uint32_t)kDirectGroups && a.n_groups <= (uint32_t)kMaxSmemGroups;
+// K3 step 1: candidate row range [lb, lb+len) of one query. `valid` = the query exists.
+__device__ __forceinline__ void query_bounds(const JoinArgs& a, const GroupTables& tb, bool valid,
+                                             uint32_t ql, uint32_t qh, uint32_t qg, uint32_t& lb,
+                                             uint32_t& len) {
   const bool in_smem = a.n_groups <= (uint32_t)kMaxSmemGroups;
-  if (in_smem) {
-    if (direct)
-      for (int g = tid; g < kDirectGroups; g += kJoinThreads) sm.g_map[g] = 0xffffu;
-    __syncthreads();
-    for (uint32_t g = tid; g < a.n_groups; g += kJoinThreads) {
-      const GroupDesc d = a.groups[g];
-      sm.g_val[g] = d.gval;
-      sm.g_nb[g] = d.nb;
-      sm.g_base[g] = d.bin_base;
-      if (direct) sm.g_map[d.gval] = (uint16_t)g;
+  const bool direct = in_smem && a.max_gval < (uint32_t)kDirectGroups;
+  lb = 0;
+  len = 0;
+  uint32_t nb = 0;
+  uint64_t bin_base = 0;
+  if (valid) {
+    if (direct) {
+      const uint32_t gi = qg < (uint32_t)kDirectGroups ? tb.g_map[qg] : 0xffffu;
+      if (gi != 0xffffu) { nb = tb.g_nb[gi]; bin_base = tb.g_base[gi]; }
+    } else if (in_smem) {
+      uint32_t lo = 0, hi = a.n_groups;
+      while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (tb.g_val[mid] < qg) lo = mid + 1; else hi = mid;
+      }
+      if (lo < a.n_groups && tb.g_val[lo] == qg) { nb = tb.g_nb[lo]; bin_base = tb.g_base[lo]; }
+    } else {
+      uint32_t lo = 0, hi = a.n_groups;
+      while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (a.groups[mid].gval < qg) lo = mid + 1; else hi = mid;
+      }
+      if (lo < a.n_groups && a.groups[lo].gval == qg) { nb = a.groups[lo].nb; bin_base = a.groups[lo].bin_base; }
     }
   }
-  __syncthreads();
+  const uint32_t b_lo = ql >> a.shift;
+  if (b_lo < nb) {  // otherwise unknown group, or q.low lies beyond every high of the group
+    uint32_t b_hi = qh >> a.shift;
+    if (b_hi >= nb) b_hi = nb - 1u;
+    const uint2 e = ldg_u2(a.dir + bin_base + b_lo);  // {lb(b_lo), ub(b_lo + 1)}: all a one-bin query needs
+    uint32_t u = e.y;
+    if (b_hi != b_lo) u = ldg_u2(a.dir + bin_base + b_hi).y;
+    lb = e.x;
+    len = u > e.x ? u - e.x : 0u;
+  }
+}
 
-  const uint32_t warps_total = gridDim.x * kJoinWarps;
-  uint32_t tile = blockIdx.x * kJoinWarps + warp;
+// K3 step 2, short ranges: the 4 queries of a lane advance together (4 independent loads per trip).
+__device__ __forceinline__ void scan_short(const JoinArgs& a, const uint32_t (&ql)[kQPT],
+                                           const uint32_t (&qh)[kQPT], const uint32_t (&lb)[kQPT],
+                                           const uint32_t (&len)[kQPT], uint32_t (&mask)[kQPT]) {
+  uint32_t max_short = 0;
+#pragma unroll
+  for (int j = 0; j < kQPT; ++j) {
+    mask[j] = 0;
+    if (len[j] <= kScalarMax && len[j] > max_short) max_short = len[j];
+  }
+  for (uint32_t k = 0; k < max_short; ++k) {
+#pragma unroll
+    for (int j = 0; j < kQPT; ++j) {
+      if (k < len[j] && len[j] <= kScalarMax) {
+        const uint2 t = ldg_u2(a.lowhigh + lb[j] + k);
+        mask[j] |= (uint32_t)overlaps(ql[j], qh[j], t.x, t.y) << k;
+      }
+    }
+  }
+}
 
-  uint32_t nql[kQPT], nqh[kQPT], nqg[kQPT];  // prefetched queries of the next tile
-  if (tile < a.n_tiles) load_queries(a, tile * kWarpTile + lane * kQPT, nql, nqh, nqg);
+// K3 step 2, long ranges: warp-cooperative scan of the rows [blb, bub): every lane takes two adjacent
+// rows per 128-bit load and keeps two loads in flight (128 rows per trip). `lowhigh` is 16-byte aligned
+// and padded by two rows, so the pair that straddles `bub` may be read.
+// EMIT = false: returns the hit count (in every lane).
+// EMIT = true : writes (qid, id) of the hits to consecutive slots from `base`, in row order.
+template <bool EMIT>
+__device__ __forceinline__ uint32_t warp_scan_range(const JoinArgs& a, uint32_t blb, uint32_t bub,
+                                                    uint32_t ql, uint32_t qh, int lane, uint64_t base,
+                                                    uint32_t qid) {
+  const uint4* pairs = reinterpret_cast<const uint4*>(a.lowhigh);
+  const uint32_t p_end = (bub + 1u) >> 1;
+  const unsigned lt = (1u << lane) - 1u;
+  uint32_t c = 0;
+  for (uint32_t p0 = blb >> 1; p0 < p_end; p0 += 64) {
+    const uint32_t pa = p0 + lane, pb = pa + 32;
+    const bool va = pa < p_end, vb = pb < p_end;
+    uint4 ta = make_uint4(0, 0, 0, 0), tb = make_uint4(0, 0, 0, 0);
+    if (va) ta = ldg_u4(pairs + pa);
+    if (vb) tb = ldg_u4(pairs + pb);
+    const uint32_t ra = pa * 2, rb = pb * 2;
+    const bool h0 = va && ra >= blb && ra < bub && overlaps(ql, qh, ta.x, ta.y);
+    const bool h1 = va && ra + 1 >= blb && ra + 1 < bub && overlaps(ql, qh, ta.z, ta.w);
+    const bool h2 = vb && rb >= blb && rb < bub && overlaps(ql, qh, tb.x, tb.y);
+    const bool h3 = vb && rb + 1 >= blb && rb + 1 < bub && overlaps(ql, qh, tb.z, tb.w);
+    if (!EMIT) {
+      c += (uint32_t)h0 + h1 + h2 + h3;
+    } else {
+      const unsigned b0 = __ballot_sync(0xffffffffu, h0), b1 = __ballot_sync(0xffffffffu, h1);
+      const unsigned b2 = __ballot_sync(0xffffffffu, h2), b3 = __ballot_sync(0xffffffffu, h3);
+      const uint32_t n_a = __popc(b0) + __popc(b1);
+      uint64_t pos = base + __popc(b0 & lt) + __popc(b1 & lt);
+      if (h0) { if (pos < a.capacity) { a.hit_target[pos] = a.ids[ra]; a.hit_query[pos] = qid; } ++pos; }
+      if (h1) { if (pos < a.capacity) { a.hit_target[pos] = a.ids[ra + 1]; a.hit_query[pos] = qid; } }
+      pos = base + n_a + __popc(b2 & lt) + __popc(b3 & lt);
+      if (h2) { if (pos < a.capacity) { a.hit_target[pos] = a.ids[rb]; a.hit_query[pos] = qid; } ++pos; }
+      if (h3) { if (pos < a.capacity) { a.hit_target[pos] = a.ids[rb + 1]; a.hit_query[pos] = qid; } }
+      base += n_a + __popc(b2) + __popc(b3);
+    }
+  }
+  if (!EMIT) {
+#pragma unroll
+    for (int off = 16; off; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+  }
+  return c;
+}
 
-  for (; tile < a.n_tiles; tile += warps_total) {
-    const uint32_t q0 = tile * (uint32_t)kWarpTile + (uint32_t)lane * kQPT;
+// K4 scatter, short ranges of one warp (128 queries): stage each hit's row at its rank among the warp's
+// short-range hits, then gather rows -> target ids with independent loads and write to consecutive
+// addresses. off[j] = output position of query j's first hit, relative to `base`.
+__device__ __forceinline__ void emit_short(const JoinArgs& a, StageBuffers& st, int warp, int lane,
+                                           const uint32_t (&mask)[kQPT], const uint32_t (&lb)[kQPT],
+                                           const uint64_t (&off)[kQPT], uint64_t base, uint32_t qid0) {
+  const uint32_t lane_hits = __popc(mask[0]) + __popc(mask[1]) + __popc(mask[2]) + __popc(mask[3]);
+  uint32_t incl = lane_hits;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const uint32_t staged_total = __shfl_sync(0xffffffffu, incl, 31);
+  const uint32_t first_slot = incl - lane_hits;
+  for (uint32_t r0 = 0; r0 < staged_total; r0 += kStage) {
+    uint32_t slot = first_slot;
+#pragma unroll
+    for (int j = 0; j < kQPT; ++j) {
+      uint32_t m = mask[j];
+      uint64_t pos = off[j];
+      while (m) {
+        const uint32_t k = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t s = slot - r0;  // wraps below the window: caught by the unsigned compare
+        if (s < (uint32_t)kStage) {
+          st.val[warp][s] = lb[j] + k;
+          st.pos[warp][s] = pos;
+          st.qi[warp][s] = (uint8_t)(lane * kQPT + j);
+        }
+        ++slot;
+        ++pos;
+      }
+    }
+    __syncwarp();
+    const uint32_t n_here = min((uint32_t)kStage, staged_total - r0);
+    for (uint32_t s = lane; s < n_here; s += 32) {
+      const uint64_t pos = base + st.pos[warp][s];
+      if (pos < a.capacity) {
+        a.hit_target[pos] = a.ids[st.val[warp][s]];
+        a.hit_query[pos] = qid0 + st.qi[warp][s];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K3: probe. No barriers inside the chunk loop.
+__global__ void __launch_bounds__(kJoinThreads, kJoinMinBlocks) probe_kernel(const JoinArgs a) {
+  __shared__ GroupTables tb;
+  __shared__ uint64_t s_warp_total[kJoinWarps];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  load_group_tables(a, tb);
+
+  const uint64_t chunk_begin = (uint64_t)blockIdx.x * a.chunk;
+  const uint64_t chunk_end = min(chunk_begin + (uint64_t)a.chunk, (uint64_t)a.n_q);
+  uint64_t acc = 0;  // hits of this lane's queries over the whole chunk
+
+  uint64_t w0 = chunk_begin + (uint64_t)warp * kWarpTile;
+  uint32_t nql[kQPT], nqh[kQPT], nqg[kQPT];  // prefetched queries of the next step
+  if (w0 < chunk_end) load_queries(a, (uint32_t)w0 + lane * kQPT, nql, nqh, nqg);
+  for (; w0 < chunk_end; w0 += kCtaTile) {
+    const uint32_t q0 = (uint32_t)w0 + (uint32_t)lane * kQPT;
     uint32_t ql[kQPT], qh[kQPT], qg[kQPT];
 #pragma unroll
     for (int j = 0; j < kQPT; ++j) { ql[j] = nql[j]; qh[j] = nqh[j]; qg[j] = nqg[j]; }
-    if (tile + warps_total < a.n_tiles)
-      load_queries(a, (tile + warps_total) * kWarpTile + lane * kQPT, nql, nqh, nqg);
+    if (w0 + kCtaTile < chunk_end) load_queries(a, q0 + kCtaTile, nql, nqh, nqg);
 
-    // ---- 1. bounds ---------------------------------------------------------------------------------
-    uint32_t lb[kQPT], len[kQPT];
+    uint32_t lb[kQPT], len[kQPT], w[kQPT];
+#pragma unroll
+    for (int j = 0; j < kQPT; ++j) query_bounds(a, tb, q0 + j < a.n_q, ql[j], qh[j], qg[j], lb[j], len[j]);
+    scan_short(a, ql, qh, lb, len, w);
 #pragma unroll
     for (int j = 0; j < kQPT; ++j) {
-      lb[j] = 0;
-      len[j] = 0;
-      uint32_t nb = 0;
-      uint64_t bin_base = 0;
-      if (q0 + j < a.n_q) {
-        if (direct) {
-          const uint32_t gi = qg[j] < (uint32_t)kDirectGroups ? sm.g_map[qg[j]] : 0xffffu;
-          if (gi != 0xffffu) { nb = sm.g_nb[gi]; bin_base = sm.g_base[gi]; }
-        } else if (in_smem) {
-          uint32_t lo = 0, hi = a.n_groups;
-          while (lo < hi) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (sm.g_val[mid] < qg[j]) lo = mid + 1; else hi = mid;
-          }
-          if (lo < a.n_groups && sm.g_val[lo] == qg[j]) { nb = sm.g_nb[lo]; bin_base = sm.g_base[lo]; }
-        } else {
-          uint32_t lo = 0, hi = a.n_groups;
-          while (lo < hi) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (a.groups[mid].gval < qg[j]) lo = mid + 1; else hi = mid;
-          }
-          if (lo < a.n_groups && a.groups[lo].gval == qg[j]) { nb = a.groups[lo].nb; bin_base = a.groups[lo].bin_base; }
-        }
-      }
-      const uint32_t b_lo = ql[j] >> a.shift;
-      if (b_lo < nb) {  // otherwise unknown group, or q.low lies beyond every high of the group
-        uint32_t b_hi1 = (qh[j] >> a.shift) + 1u;
-        if (b_hi1 > nb) b_hi1 = nb;
-        const uint32_t l = a.dir[bin_base + b_lo].x;
-        const uint32_t u = a.dir[bin_base + b_hi1].y;
-        lb[j] = l;
-        len[j] = u > l ? u - l : 0u;
+      acc += __popc(w[j]);
+      unsigned big = __ballot_sync(0xffffffffu, len[j] > kScalarMax);
+      while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const uint32_t blb = __shfl_sync(0xffffffffu, lb[j], src);
+        const uint32_t bub = blb + __shfl_sync(0xffffffffu, len[j], src);
+        const uint32_t bql = __shfl_sync(0xffffffffu, ql[j], src);
+        const uint32_t bqh = __shfl_sync(0xffffffffu, qh[j], src);
+        const uint32_t c = warp_scan_range<false>(a, blb, bub, bql, bqh, lane, 0, 0);
+        if (lane == src) { w[j] = kBigFlag | c; acc += c; }
       }
     }
+    // state: 8 bytes per query, 128-bit stores (the arrays are padded to a multiple of kCtaTile)
+    *reinterpret_cast<uint4*>(a.st_lb + q0) = make_uint4(lb[0], lb[1], lb[2], lb[3]);
+    *reinterpret_cast<uint4*>(a.st_w + q0) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) acc += shfl_u64(acc, lane ^ off);
+  if (lane == 0) s_warp_total[warp] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    uint64_t t = 0;
+#pragma unroll
+    for (int w = 0; w < kJoinWarps; ++w) t += s_warp_total[w];
+    a.cta_total[blockIdx.x] = t;
+  }
+}
 
-    // ---- 2. count ----------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------
+// K4: prefix sum + scatter. One barrier per 1024 queries, no waiting on other CTAs.
+template <bool EMIT>
+__global__ void __launch_bounds__(kJoinThreads, kJoinMinBlocks) emit_kernel(const JoinArgs a) {
+  __shared__ GroupTables tb;
+  __shared__ StageBuffers st;
+  __shared__ uint64_t s_warp_total[2][kJoinWarps];
+  __shared__ uint64_t s_red[kJoinWarps];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (EMIT) load_group_tables(a, tb);  // only the long-range re-scan needs them
+
+  // global base of this chunk = hits of all chunks before it
+  uint64_t part = 0;
+  for (uint32_t c = tid; c < blockIdx.x; c += kJoinThreads) part += a.cta_total[c];
+#pragma unroll
+  for (int off = 16; off; off >>= 1) part += shfl_u64(part, lane ^ off);
+  if (lane == 0) s_red[warp] = part;
+  __syncthreads();
+  uint64_t running = 0;
+#pragma unroll
+  for (int w = 0; w < kJoinWarps; ++w) running += s_red[w];
+
+  const uint64_t chunk_begin = (uint64_t)blockIdx.x * a.chunk;
+  const uint64_t chunk_end = min(chunk_begin + (uint64_t)a.chunk, (uint64_t)a.n_q);
+  if (blockIdx.x == gridDim.x - 1 && tid == 0) {  // grand total
+    const uint64_t t = running + a.cta_total[blockIdx.x];
+    a.offsets[a.n_q] = t;
+    if (a.total) *a.total = t;
+  }
+
+  uint4 n_lb = make_uint4(0, 0, 0, 0), n_w = make_uint4(0, 0, 0, 0);  // prefetched state of the next step
+  {
+    const uint64_t q = chunk_begin + (uint64_t)tid * kQPT;
+    if (q < chunk_end) {
+      n_lb = *reinterpret_cast<const uint4*>(a.st_lb + q);
+      n_w = *reinterpret_cast<const uint4*>(a.st_w + q);
+    }
+  }
+  int par = 0;
+  for (uint64_t t0 = chunk_begin; t0 < chunk_end; t0 += kCtaTile, par ^= 1) {
+    const uint32_t w0 = (uint32_t)t0 + (uint32_t)warp * kWarpTile;
+    const uint32_t q0 = w0 + (uint32_t)lane * kQPT;
+    const uint32_t lb[kQPT] = {n_lb.x, n_lb.y, n_lb.z, n_lb.w};
+    const uint32_t w[kQPT] = {n_w.x, n_w.y, n_w.z, n_w.w};
+    if (t0 + kCtaTile + (uint64_t)tid * kQPT < chunk_end) {
+      n_lb = *reinterpret_cast<const uint4*>(a.st_lb + q0 + kCtaTile);
+      n_w = *reinterpret_cast<const uint4*>(a.st_w + q0 + kCtaTile);
+    } else {
+      n_lb = make_uint4(0, 0, 0, 0);
+      n_w = make_uint4(0, 0, 0, 0);
+    }
     uint32_t cnt[kQPT], mask[kQPT];
-    uint32_t max_short = 0;
+    bool lane_big = false;
 #pragma unroll
     for (int j = 0; j < kQPT; ++j) {
-      cnt[j] = 0;
-      mask[j] = 0;
-      if (len[j] <= kScalarMax && len[j] > max_short) max_short = len[j];
+      const bool big = (w[j] & kBigFlag) != 0;
+      lane_big |= big;
+      mask[j] = big ? 0u : w[j];
+      cnt[j] = big ? (w[j] & ~kBigFlag) : (uint32_t)__popc(w[j]);
     }
-    // the 4 queries of a lane advance together: 4 independent loads per trip
-    for (uint32_t k = 0; k < max_short; ++k) {
+    // ---- prefix: lane -> warp (shuffles) -> CTA step (shared memory, one barrier) -> running base ----
+    const uint64_t lane_sum = (uint64_t)cnt[0] + cnt[1] + cnt[2] + cnt[3];
+    uint64_t incl = lane_sum;
 #pragma unroll
-      for (int j = 0; j < kQPT; ++j) {
-        if (k < len[j] && len[j] <= kScalarMax) {
-          const uint2 t = a.lowhigh[lb[j] + k];
-          mask[j] |= (uint32_t)overlaps(ql[j], qh[j], t) << k;
-        }
-      }
+    for (int o = 1; o < 32; o <<= 1) {
+      uint64_t v = __shfl_up_sync(0xffffffffu, (unsigned long long)incl, o);
+      if (lane >= o) incl += v;
     }
+    if (lane == 31) s_warp_total[par][warp] = incl;
+    __syncthreads();
+    uint64_t warp_base = running;
 #pragma unroll
-    for (int j = 0; j < kQPT; ++j) cnt[j] = __popc(mask[j]);
-    bool any_big = false;
-    if (MODE != kModeScatter) {
-#pragma unroll
-      for (int j = 0; j < kQPT; ++j) {
-        unsigned big = __ballot_sync(0xffffffffu, len[j] > kScalarMax);
-        any_big |= (big != 0);
-        while (big) {
-          const int src = __ffs(big) - 1;
-          big &= big - 1;
-          const uint32_t blb = __shfl_sync(0xffffffffu, lb[j], src);
-          const uint32_t bub = blb + __shfl_sync(0xffffffffu, len[j], src);
-          const uint32_t bql = __shfl_sync(0xffffffffu, ql[j], src);
-          const uint32_t bqh = __shfl_sync(0xffffffffu, qh[j], src);
-          uint32_t c = 0;
-          for (uint32_t r = blb + lane; r < bub; r += 32) c += overlaps(bql, bqh, a.lowhigh[r]);
-#pragma unroll
-          for (int off = 16; off; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
-          if (lane == src) cnt[j] = c;
-        }
-      }
+    for (int ww = 0; ww < kJoinWarps; ++ww) {
+      const uint64_t t = s_warp_total[par][ww];
+      if (ww < warp) warp_base += t;
+      running += t;
     }
-
-    if (MODE == kModeAny) {
-#pragma unroll
-      for (int j = 0; j < kQPT; ++j)
-        if (q0 + j < a.n_q) a.any[q0 + j] = cnt[j] ? 1 : 0;
-      continue;
-    }
-
-    // ---- 3. prefix sum -> CSR offsets --------------------------------------------------------------
-    uint64_t off[kQPT];
-    if (kNeedsPrefix) {
-      const uint64_t lane_sum = (uint64_t)cnt[0] + cnt[1] + cnt[2] + cnt[3];
-      uint64_t incl = lane_sum;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        uint64_t v = shfl_up_u64(incl, o);
-        if (lane >= o) incl += v;
-      }
-      const uint64_t tile_total = shfl_u64(incl, 31);
-      const uint64_t base = lookback_exclusive<SumOp>(a.status, tile, tile_total);
-      if (tile == a.n_tiles - 1 && lane == 0) {
-        a.offsets[a.n_q] = base + tile_total;
-        if (a.total) *a.total = base + tile_total;
-      }
-      uint64_t run = base + incl - lane_sum;
+    uint64_t off[kQPT];  // relative to warp_base
+    {
+      uint64_t run = incl - lane_sum;
 #pragma unroll
       for (int j = 0; j < kQPT; ++j) { off[j] = run; run += cnt[j]; }
-      if (a.vec_ok && q0 + kQPT <= a.n_q) {
-        ulonglong2* o = reinterpret_cast<ulonglong2*>(a.offsets + q0);
-        o[0] = make_ulonglong2(off[0], off[1]);
-        o[1] = make_ulonglong2(off[2], off[3]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < kQPT; ++j) if (q0 + j < a.n_q) a.offsets[q0 + j] = off[j];
-      }
+    }
+    if (a.vec_ok && q0 + kQPT <= a.n_q) {
+      ulonglong2* o = reinterpret_cast<ulonglong2*>(a.offsets + q0);
+      o[0] = make_ulonglong2(warp_base + off[0], warp_base + off[1]);
+      o[1] = make_ulonglong2(warp_base + off[2], warp_base + off[3]);
     } else {
 #pragma unroll
-      for (int j = 0; j < kQPT; ++j) off[j] = (q0 + j < a.n_q) ? a.offsets[q0 + j] : 0ull;
+      for (int j = 0; j < kQPT; ++j) if (q0 + j < a.n_q) a.offsets[q0 + j] = warp_base + off[j];
     }
-    if (!kEmits) continue;
+    if (!EMIT) continue;
 
-    // ---- 4. scatter --------------------------------------------------------------------------------
-    // short ranges: rank of each hit among the tile's short-range hits -> staging slot
-    {
-      const uint32_t lane_hits = __popc(mask[0]) + __popc(mask[1]) + __popc(mask[2]) + __popc(mask[3]);
-      uint32_t incl = lane_hits;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-      }
-      const uint32_t staged_total = __shfl_sync(0xffffffffu, incl, 31);
-      const uint32_t first_slot = incl - lane_hits;
-      const uint32_t qid0 = a.qid_base + tile * (uint32_t)kWarpTile;
-      for (uint32_t r0 = 0; r0 < staged_total; r0 += kStage) {
-        uint32_t slot = first_slot;
-#pragma unroll
-        for (int j = 0; j < kQPT; ++j) {
-          uint32_t m = mask[j];
-          uint64_t pos = off[j];
-          while (m) {
-            const uint32_t k = __ffs(m) - 1;
-            m &= m - 1;
-            const uint32_t s = slot - r0;  // wraps below the window: caught by the unsigned compare
-            if (s < (uint32_t)kStage) {
-              sm.st_row[warp][s] = lb[j] + k;
-              sm.st_pos[warp][s] = pos;
-              sm.st_qi[warp][s] = (uint8_t)(lane * kQPT + j);
-            }
-            ++slot;
-            ++pos;
-          }
-        }
-        __syncwarp();
-        const uint32_t n_here = min((uint32_t)kStage, staged_total - r0);
-        for (uint32_t s = lane; s < n_here; s += 32) {
-          const uint64_t pos = sm.st_pos[warp][s];
-          if (pos < a.capacity) {
-            a.hit_target[pos] = a.ids[sm.st_row[warp][s]];
-            a.hit_query[pos] = qid0 + sm.st_qi[warp][s];
-          }
-        }
-        __syncwarp();
-      }
-    }
-    // long ranges: warp-cooperative re-scan with ballot/popc compaction
-    if (MODE == kModeScatter) {
-#pragma unroll
-      for (int j = 0; j < kQPT; ++j) any_big |= __any_sync(0xffffffffu, len[j] > kScalarMax);
-    }
-    if (any_big) {
+    // ---- scatter ------------------------------------------------------------------------------------
+    emit_short(a, st, warp, lane, mask, lb, off, warp_base, a.qid_base + w0);
+    if (__any_sync(0xffffffffu, lane_big)) {
+      uint32_t ql[kQPT], qh[kQPT], qg[kQPT];
+      load_queries(a, q0, ql, qh, qg);
 #pragma unroll
       for (int j = 0; j < kQPT; ++j) {
+        unsigned big = __ballot_sync(0xffffffffu, (w[j] & kBigFlag) != 0);
+        while (big) {
+          const int src = __ffs(big) - 1;
+          big &= big - 1;
+          uint32_t blb = 0, blen = 0;  // the owner recomputes its bounds (two cached 8-byte loads)
+          if (lane == src) query_bounds(a, tb, true, ql[j], qh[j], qg[j], blb, blen);
+          blb = __shfl_sync(0xffffffffu, blb, src);
+          const uint32_t bub = blb + __shfl_sync(0xffffffffu, blen, src);
+          const uint32_t bql = __shfl_sync(0xffffffffu, ql[j], src);
+          const uint32_t bqh = __shfl_sync(0xffffffffu, qh[j], src);
+          const uint64_t qbase = warp_base + shfl_u64(off[j], src);
+          warp_scan_range<true>(a, blb, bub, bql, bqh, lane, qbase, a.qid_base + w0 + (uint32_t)src * kQPT + j);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Scatter with caller-supplied offsets / any-overlap bit: static tiles, no prefix step.
+template <int MODE>
+__global__ void __launch_bounds__(kJoinThreads, kJoinMinBlocks) direct_kernel(const JoinArgs a) {
+  __shared__ GroupTables tb;
+  __shared__ StageBuffers st;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  load_group_tables(a, tb);
+  const uint32_t n_tiles = (a.n_q + kCtaTile - 1) / kCtaTile;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t w0 = tile * (uint32_t)kCtaTile + (uint32_t)warp * kWarpTile;
+    const uint32_t q0 = w0 + (uint32_t)lane * kQPT;
+    uint32_t ql[kQPT], qh[kQPT], qg[kQPT], lb[kQPT], len[kQPT], mask[kQPT];
+    load_queries(a, q0, ql, qh, qg);
+#pragma unroll
+    for (int j = 0; j < kQPT; ++j) query_bounds(a, tb, q0 + j < a.n_q, ql[j], qh[j], qg[j], lb[j], len[j]);
+    scan_short(a, ql, qh, lb, len, mask);
+    if (MODE == kModeAny) {
+#pragma unroll
+      for (int j = 0; j < kQPT; ++j) {
+        uint32_t c = mask[j];
         unsigned big = __ballot_sync(0xffffffffu, len[j] > kScalarMax);
         while (big) {
           const int src = __ffs(big) - 1;
           big &= big - 1;
           const uint32_t blb = __shfl_sync(0xffffffffu, lb[j], src);
           const uint32_t bub = blb + __shfl_sync(0xffffffffu, len[j], src);
-          const uint32_t bql = __shfl_sync(0xffffffffu, ql[j], src);
-          const uint32_t bqh = __shfl_sync(0xffffffffu, qh[j], src);
-          uint64_t base = shfl_u64(off[j], src);
-          const uint32_t qid = a.qid_base + tile * (uint32_t)kWarpTile + (uint32_t)src * kQPT + j;
-          for (uint32_t r0 = blb; r0 < bub; r0 += 32) {
-            const uint32_t r = r0 + lane;
-            const bool hit = (r < bub) && overlaps(bql, bqh, a.lowhigh[r < bub ? r : blb]);
-            const unsigned bal = __ballot_sync(0xffffffffu, hit);
-            if (hit) {
-              const uint64_t pos = base + __popc(bal & ((1u << lane) - 1u));
-              if (pos < a.capacity) {
-                a.hit_target[pos] = a.ids[r];
-                a.hit_query[pos] = qid;
-              }
-            }
-            base += __popc(bal);
-          }
+          const uint32_t n = warp_scan_range<false>(a, blb, bub, __shfl_sync(0xffffffffu, ql[j], src),
+                                                    __shfl_sync(0xffffffffu, qh[j], src), lane, 0, 0);
+          if (lane == src) c = n;
         }
+        if (q0 + j < a.n_q) a.any[q0 + j] = c ? 1 : 0;
+      }
+      continue;
+    }
+    uint64_t off[kQPT];
+#pragma unroll
+    for (int j = 0; j < kQPT; ++j) off[j] = (q0 + j < a.n_q) ? a.offsets[q0 + j] : 0ull;
+    emit_short(a, st, warp, lane, mask, lb, off, 0, a.qid_base + w0);
+#pragma unroll
+    for (int j = 0; j < kQPT; ++j) {
+      unsigned big = __ballot_sync(0xffffffffu, len[j] > kScalarMax);
+      while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const uint32_t blb = __shfl_sync(0xffffffffu, lb[j], src);
+        const uint32_t bub = blb + __shfl_sync(0xffffffffu, len[j], src);
+        warp_scan_range<true>(a, blb, bub, __shfl_sync(0xffffffffu, ql[j], src),
+                              __shfl_sync(0xffffffffu, qh[j], src), lane, shfl_u64(off[j], src),
+                              a.qid_base + w0 + (uint32_t)src * kQPT + j);
       }
     }
   }
@@ -341,28 +536,19 @@ __global__ void __launch_bounds__(kJoinThreads) join_kernel(const JoinArgs a) {
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// resident CTAs per SM of each mode x SM count, per device (queried once)
-static int persistent_grid(int device, int mode) {
-  static std::atomic<int> cache[64][4];
+static int sm_count(int device) {
+  static std::atomic<int> cache[64];
   if (device >= 0 && device < 64) {
-    int v = cache[device][mode].load(std::memory_order_relaxed);
+    int v = cache[device].load(std::memory_order_relaxed);
     if (v > 0) return v;
   }
-  int per_sm = 0, sms = 0;
-  cudaError_t e = cudaSuccess;
-  switch (mode) {
-    case kModeCount: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, join_kernel<kModeCount>, kJoinThreads, 0); break;
-    case kModeScatter: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, join_kernel<kModeScatter>, kJoinThreads, 0); break;
-    case kModeFused: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, join_kernel<kModeFused>, kJoinThreads, 0); break;
-    default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, join_kernel<kModeAny>, kJoinThreads, 0); break;
-  }
-  if (e != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) {
     cudaGetLastError();
-    return 0;
+    return 148;
   }
-  int v = per_sm * sms;
-  if (device >= 0 && device < 64 && v > 0) cache[device][mode].store(v, std::memory_order_relaxed);
-  return v;
+  if (device >= 0 && device < 64) cache[device].store(sms, std::memory_order_relaxed);
+  return sms;
 }
 
 int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_qgroup,
@@ -392,7 +578,7 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
   a.qlow = d_qlow;
   a.qhigh = d_qhigh;
   a.n_q = (uint32_t)n_q;
-  a.n_tiles = (uint32_t)((n_q + kWarpTile - 1) / kWarpTile);
+  a.chunk = 0;
   a.vec_ok = aligned16(d_qlow) && aligned16(d_qhigh) && (!d_qgroup || aligned16(d_qgroup)) &&
              (!d_offsets || aligned16(d_offsets));
   a.offsets = d_offsets;
@@ -402,27 +588,35 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
   a.total = d_total;
   a.any = d_any;
   a.qid_base = query_id_base;
-  a.status = nullptr;
-  // Persistent launch: the look-back spins on predecessor tiles, so every CTA must be resident.
-  const int resident = persistent_grid(ix->device, mode);
-  if (resident <= 0) { set_error("cannot determine a resident grid for the join kernel"); return BCU_E_CUDA; }
-  const uint32_t ctas_needed = (a.n_tiles + kJoinWarps - 1) / kJoinWarps;
-  const uint32_t grid = ctas_needed < (uint32_t)resident ? ctas_needed : (uint32_t)resident;
+  a.st_lb = nullptr;
+  a.st_w = nullptr;
+  a.cta_total = nullptr;
+  const uint64_t n_tiles = (n_q + kCtaTile - 1) / kCtaTile;
+  const uint64_t cta_budget = (uint64_t)sm_count(ix->device) * kJoinMinBlocks * 2;  // two waves of CTAs
+  if (!prefix) {
+    const unsigned grid = (unsigned)(n_tiles < cta_budget ? n_tiles : cta_budget);
+    if (mode == kModeScatter) direct_kernel<kModeScatter><<<grid, kJoinThreads, 0, stream>>>(a);
+    else direct_kernel<kModeAny><<<grid, kJoinThreads, 0, stream>>>(a);
+    BCU_LAUNCHED();
+    return BCU_OK;
+  }
+  // chunking shared by probe and emit: contiguous runs of whole CTA steps
+  const uint64_t tiles_per_cta = (n_tiles + cta_budget - 1) / cta_budget;
+  const unsigned grid = (unsigned)((n_tiles + tiles_per_cta - 1) / tiles_per_cta);
+  a.chunk = (uint32_t)(tiles_per_cta * kCtaTile);
+  const uint64_t padded = n_tiles * kCtaTile;
   void* scratch = nullptr;
-  if (prefix) {
-    size_t bytes = (size_t)a.n_tiles * 8;
-    BCU_CUDA(cudaMallocAsync(&scratch, bytes, stream));
-    BCU_CUDA(cudaMemsetAsync(scratch, 0, bytes, stream));
-    a.status = reinterpret_cast<uint64_t*>(scratch);
-  }
-  switch (mode) {
-    case kModeCount: join_kernel<kModeCount><<<grid, kJoinThreads, 0, stream>>>(a); break;
-    case kModeScatter: join_kernel<kModeScatter><<<grid, kJoinThreads, 0, stream>>>(a); break;
-    case kModeFused: join_kernel<kModeFused><<<grid, kJoinThreads, 0, stream>>>(a); break;
-    default: join_kernel<kModeAny><<<grid, kJoinThreads, 0, stream>>>(a); break;
-  }
+  const uint64_t grid_even = ((uint64_t)grid + 1) & ~1ull;  // keeps the state arrays 16-byte aligned
+  BCU_CUDA(cudaMallocAsync(&scratch, padded * 8 + grid_even * 8, stream));
+  a.cta_total = reinterpret_cast<uint64_t*>(scratch);
+  a.st_lb = reinterpret_cast<uint32_t*>(a.cta_total + grid_even);
+  a.st_w = a.st_lb + padded;
+  probe_kernel<<<grid, kJoinThreads, 0, stream>>>(a);
   BCU_LAUNCHED();
-  if (scratch) BCU_CUDA(cudaFreeAsync(scratch, stream));
+  if (mode == kModeFused) emit_kernel<true><<<grid, kJoinThreads, 0, stream>>>(a);
+  else emit_kernel<false><<<grid, kJoinThreads, 0, stream>>>(a);
+  BCU_LAUNCHED();
+  BCU_CUDA(cudaFreeAsync(scratch, stream));
   return BCU_OK;
 }
 

@@ -48,7 +48,7 @@ typedef enum bcu_status {
   BCU_E_CUDA = -2,     /* CUDA runtime/driver error (message has the CUDA string)   */
   BCU_E_NOMEM = -3,    /* host or device allocation failed                          */
   BCU_E_CAPACITY = -4, /* caller-provided pair buffer too small; *total = required  */
-  BCU_E_LIMIT = -5     /* input exceeds a documented limit (n_t, n_q <= 2^32 - 2)   */
+  BCU_E_LIMIT = -5     /* input exceeds a documented limit (n_t <= 2^31-1, n_q <= 2^32-2) */
 } bcu_status;
 
 typedef struct bcu_index bcu_index; /* opaque; lives on one device */
