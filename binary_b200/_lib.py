@@ -46,6 +46,7 @@ SIGNATURES = {
     "bcu_query_count": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp, u64p]),
     "bcu_query_scatter": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp, vp, vp]),
     "bcu_join": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp, C.c_uint64, vp, vp, u64p]),
+    "bcu_trim": (C.c_int, []),
     "bcu_query_any": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp]),
     "bcu_query_count_dev": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp, vp]),
     "bcu_query_scatter_dev": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp, vp, vp, vp]),

@@ -186,45 +186,6 @@ extern "C" int bcu_query_scatter(const bcu_index* ix, uint64_t n_q, const uint32
   return BCU_OK;
 }
 
-extern "C" int bcu_join(const bcu_index* ix, uint64_t n_q, const uint32_t* qgroup, const uint32_t* qlow,
-                        const uint32_t* qhigh, uint64_t* offsets, uint64_t pair_capacity,
-                        uint32_t* hit_query, uint32_t* hit_target, uint64_t* total) {
-  BCU_TRY(check_query_args("bcu_join", ix, n_q, qlow, qhigh));
-  if (!offsets || !total) { set_error("bcu_join: offsets/total are NULL"); return BCU_E_INVALID; }
-  if (pair_capacity && (!hit_query || !hit_target)) {
-    set_error("bcu_join: pair buffers are NULL");
-    return BCU_E_INVALID;
-  }
-  DeviceGuard guard(ix->device);
-  Staging st;
-  BCU_TRY(st.init());
-  uint32_t *d_g, *d_l, *d_h, *d_hq, *d_ht;
-  uint64_t *d_off, *d_total;
-  BCU_TRY(st.upload(&d_g, qgroup, n_q));
-  BCU_TRY(st.upload(&d_l, qlow, n_q));
-  BCU_TRY(st.upload(&d_h, qhigh, n_q));
-  BCU_TRY(st.alloc(&d_off, n_q + 1));
-  BCU_TRY(st.alloc(&d_total, 1));
-  BCU_TRY(st.alloc(&d_hq, pair_capacity));
-  BCU_TRY(st.alloc(&d_ht, pair_capacity));
-  BCU_TRY(launch_join(ix, kModeFused, n_q, d_g, d_l, d_h, d_off, pair_capacity, d_hq, d_ht, d_total, nullptr,
-                      0, st.stream));
-  BCU_CUDA(cudaMemcpyAsync(offsets, d_off, (n_q + 1) * 8, cudaMemcpyDeviceToHost, st.stream));
-  BCU_CUDA(cudaStreamSynchronize(st.stream));
-  *total = offsets[n_q];
-  if (*total > pair_capacity) {
-    set_error("bcu_join: %llu pairs exceed pair_capacity %llu", (unsigned long long)*total,
-              (unsigned long long)pair_capacity);
-    return BCU_E_CAPACITY;
-  }
-  if (*total) {
-    BCU_CUDA(cudaMemcpyAsync(hit_query, d_hq, *total * 4, cudaMemcpyDeviceToHost, st.stream));
-    BCU_CUDA(cudaMemcpyAsync(hit_target, d_ht, *total * 4, cudaMemcpyDeviceToHost, st.stream));
-    BCU_CUDA(cudaStreamSynchronize(st.stream));
-  }
-  return BCU_OK;
-}
-
 extern "C" int bcu_query_any(const bcu_index* ix, uint64_t n_q, const uint32_t* qgroup,
                              const uint32_t* qlow, const uint32_t* qhigh, uint8_t* any) {
   BCU_TRY(check_query_args("bcu_query_any", ix, n_q, qlow, qhigh));

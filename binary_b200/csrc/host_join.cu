@@ -1,0 +1,184 @@
+// bcu_join with HOST buffers: the end-to-end path a caller of the reference's find_overlaps loop
+// (sv2nl mapper.hpp:207-218) switches to. The batch is cut into chunks that flow through three streams
+//   copy-in (H2D queries)  ->  run (probe + emit kernels, join.cu)  ->  copy-out (D2H offsets + pairs)
+// so PCIe transfers in both directions overlap the kernels. Offsets are global across chunks: each
+// chunk's emit kernel starts from the previous chunk's running total, which stays on the device.
+// Device staging buffers and streams are cached per host thread and device (grow-only; bcu_trim frees).
+#include <algorithm>
+#include <memory>
+#include <vector>
+
+#include "common.cuh"
+
+namespace bcu {
+
+constexpr uint64_t kHostChunk = 2u << 20;  // queries per pipeline chunk (multiple of the CTA step)
+constexpr int kMaxDevices = 64;
+
+struct HostCtx {
+  int device = -1;
+  cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+  uint32_t *d_qg = nullptr, *d_ql = nullptr, *d_qh = nullptr;
+  uint64_t cap_qg = 0, cap_ql = 0, cap_qh = 0;
+  uint64_t* d_off = nullptr;
+  uint64_t cap_off = 0;
+  uint32_t *d_hq = nullptr, *d_ht = nullptr;
+  uint64_t cap_hq = 0, cap_ht = 0;
+  uint64_t* d_totals = nullptr;
+  uint64_t* h_totals = nullptr;  // pinned
+  uint64_t cap_chunks = 0;
+  std::vector<cudaEvent_t> ev_in, ev_run;
+
+  void release() {
+    cudaFree(d_qg); cudaFree(d_ql); cudaFree(d_qh); cudaFree(d_off); cudaFree(d_hq); cudaFree(d_ht);
+    cudaFree(d_totals);
+    if (h_totals) cudaFreeHost(h_totals);
+    d_qg = d_ql = d_qh = d_hq = d_ht = nullptr;
+    d_off = d_totals = h_totals = nullptr;
+    cap_qg = cap_ql = cap_qh = cap_off = cap_hq = cap_ht = cap_chunks = 0;
+    for (cudaEvent_t e : ev_in) cudaEventDestroy(e);
+    for (cudaEvent_t e : ev_run) cudaEventDestroy(e);
+    ev_in.clear();
+    ev_run.clear();
+    if (s_in) cudaStreamDestroy(s_in);
+    if (s_run) cudaStreamDestroy(s_run);
+    if (s_out) cudaStreamDestroy(s_out);
+    s_in = s_run = s_out = nullptr;
+    cudaGetLastError();
+  }
+  ~HostCtx() { release(); }
+
+  template <class T> int grow(T** p, uint64_t* cap, uint64_t need) {
+    if (need <= *cap) return BCU_OK;
+    cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    const uint64_t want = need + need / 4;  // headroom: batches of similar size do not reallocate
+    BCU_CUDA(cudaMalloc((void**)p, std::max<uint64_t>(want, 1) * sizeof(T)));
+    *cap = want;
+    return BCU_OK;
+  }
+
+  int prepare(int dev, uint64_t n_q, uint64_t pair_capacity, uint64_t n_chunks, bool has_group) {
+    device = dev;
+    if (!s_in) {
+      BCU_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+      BCU_CUDA(cudaStreamCreateWithFlags(&s_run, cudaStreamNonBlocking));
+      BCU_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    }
+    if (has_group) BCU_TRY(grow(&d_qg, &cap_qg, n_q));
+    BCU_TRY(grow(&d_ql, &cap_ql, n_q));
+    BCU_TRY(grow(&d_qh, &cap_qh, n_q));
+    BCU_TRY(grow(&d_off, &cap_off, n_q + 1));
+    BCU_TRY(grow(&d_hq, &cap_hq, pair_capacity));
+    BCU_TRY(grow(&d_ht, &cap_ht, pair_capacity));
+    if (n_chunks > cap_chunks) {
+      cudaFree(d_totals);
+      if (h_totals) cudaFreeHost(h_totals);
+      d_totals = h_totals = nullptr;
+      cap_chunks = 0;
+      BCU_CUDA(cudaMalloc((void**)&d_totals, n_chunks * 8));
+      BCU_CUDA(cudaHostAlloc((void**)&h_totals, n_chunks * 8, cudaHostAllocDefault));
+      cap_chunks = n_chunks;
+    }
+    while (ev_in.size() < n_chunks) {
+      cudaEvent_t a, b;
+      BCU_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+      BCU_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+      ev_in.push_back(a);
+      ev_run.push_back(b);
+    }
+    return BCU_OK;
+  }
+};
+
+static HostCtx* host_ctx(int device) {
+  static thread_local std::unique_ptr<HostCtx> ctx[kMaxDevices];
+  if (device < 0 || device >= kMaxDevices) return nullptr;
+  if (!ctx[device]) ctx[device].reset(new (std::nothrow) HostCtx());
+  return ctx[device].get();
+}
+
+void trim_host_ctx() {
+  for (int d = 0; d < kMaxDevices; ++d) {
+    HostCtx* c = host_ctx(d);
+    if (c && c->device >= 0) {
+      DeviceGuard guard(c->device);
+      c->release();
+    }
+  }
+}
+
+}  // namespace bcu
+
+using namespace bcu;
+
+extern "C" int bcu_trim(void) {
+  trim_host_ctx();
+  return BCU_OK;
+}
+
+extern "C" int bcu_join(const bcu_index* ix, uint64_t n_q, const uint32_t* qgroup, const uint32_t* qlow,
+                        const uint32_t* qhigh, uint64_t* offsets, uint64_t pair_capacity,
+                        uint32_t* hit_query, uint32_t* hit_target, uint64_t* total) {
+  if (!ix) { set_error("bcu_join: index is NULL"); return BCU_E_INVALID; }
+  if (n_q && (!qlow || !qhigh)) { set_error("bcu_join: qlow/qhigh are NULL"); return BCU_E_INVALID; }
+  if (n_q > 0xfffffffeull) { set_error("bcu_join: n_q exceeds 2^32-2"); return BCU_E_LIMIT; }
+  if (!offsets || !total) { set_error("bcu_join: offsets/total are NULL"); return BCU_E_INVALID; }
+  if (pair_capacity && (!hit_query || !hit_target)) {
+    set_error("bcu_join: pair buffers are NULL");
+    return BCU_E_INVALID;
+  }
+  *total = 0;
+  if (n_q == 0 || ix->n == 0) {
+    std::fill(offsets, offsets + n_q + 1, 0ull);
+    return BCU_OK;
+  }
+  DeviceGuard guard(ix->device);
+  if (!guard.ok) { set_error("bcu_join: cannot select CUDA device %d", ix->device); return BCU_E_CUDA; }
+  HostCtx* c = host_ctx(ix->device);
+  if (!c) { set_error("bcu_join: host context allocation failed"); return BCU_E_NOMEM; }
+  const uint64_t n_chunks = (n_q + kHostChunk - 1) / kHostChunk;
+  BCU_TRY(c->prepare(ix->device, n_q, pair_capacity, n_chunks, qgroup != nullptr));
+
+  // 1. queue every chunk's H2D copies and kernels; nothing here blocks the host
+  for (uint64_t i = 0; i < n_chunks; ++i) {
+    const uint64_t b = i * kHostChunk, n = std::min(kHostChunk, n_q - b);
+    if (qgroup) BCU_CUDA(cudaMemcpyAsync(c->d_qg + b, qgroup + b, n * 4, cudaMemcpyHostToDevice, c->s_in));
+    BCU_CUDA(cudaMemcpyAsync(c->d_ql + b, qlow + b, n * 4, cudaMemcpyHostToDevice, c->s_in));
+    BCU_CUDA(cudaMemcpyAsync(c->d_qh + b, qhigh + b, n * 4, cudaMemcpyHostToDevice, c->s_in));
+    BCU_CUDA(cudaEventRecord(c->ev_in[i], c->s_in));
+    BCU_CUDA(cudaStreamWaitEvent(c->s_run, c->ev_in[i], 0));
+    BCU_TRY(launch_join(ix, kModeFused, n, qgroup ? c->d_qg + b : nullptr, c->d_ql + b, c->d_qh + b,
+                        c->d_off + b, pair_capacity, c->d_hq, c->d_ht, c->d_totals + i, nullptr,
+                        (uint32_t)b, c->s_run, i ? c->d_totals + (i - 1) : nullptr));
+    BCU_CUDA(cudaMemcpyAsync(c->h_totals + i, c->d_totals + i, 8, cudaMemcpyDeviceToHost, c->s_run));
+    BCU_CUDA(cudaEventRecord(c->ev_run[i], c->s_run));
+  }
+  // 2. as each chunk finishes, its running total tells how many pairs to bring back
+  uint64_t done_pairs = 0;
+  for (uint64_t i = 0; i < n_chunks; ++i) {
+    const uint64_t b = i * kHostChunk, n = std::min(kHostChunk, n_q - b);
+    BCU_CUDA(cudaEventSynchronize(c->ev_run[i]));
+    const uint64_t t = c->h_totals[i];
+    BCU_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_run[i], 0));
+    const uint64_t n_off = n + (i + 1 == n_chunks ? 1 : 0);
+    BCU_CUDA(cudaMemcpyAsync(offsets + b, c->d_off + b, n_off * 8, cudaMemcpyDeviceToHost, c->s_out));
+    const uint64_t upto = std::min(t, pair_capacity);
+    if (upto > done_pairs) {
+      BCU_CUDA(cudaMemcpyAsync(hit_query + done_pairs, c->d_hq + done_pairs, (upto - done_pairs) * 4,
+                               cudaMemcpyDeviceToHost, c->s_out));
+      BCU_CUDA(cudaMemcpyAsync(hit_target + done_pairs, c->d_ht + done_pairs, (upto - done_pairs) * 4,
+                               cudaMemcpyDeviceToHost, c->s_out));
+      done_pairs = upto;
+    }
+    *total = t;
+  }
+  BCU_CUDA(cudaStreamSynchronize(c->s_out));
+  if (*total > pair_capacity) {
+    set_error("bcu_join: %llu pairs exceed pair_capacity %llu", (unsigned long long)*total,
+              (unsigned long long)pair_capacity);
+    return BCU_E_CAPACITY;
+  }
+  return BCU_OK;
+}

@@ -68,6 +68,7 @@ struct JoinArgs {
   uint32_t* st_lb;      // [n_q rounded up to kCtaTile] probe state: first candidate row
   uint32_t* st_w;       // [same] probe state: hit bitmask, or kBigFlag | hit count
   uint64_t* cta_total;  // [gridDim.x] hits per chunk
+  const uint64_t* base_in;  // optional: offset of the batch's first pair (chunked host pipeline)
 };
 
 struct GroupTables {
@@ -379,7 +380,7 @@ __global__ void __launch_bounds__(kJoinThreads, kJoinMinBlocks) emit_kernel(cons
   for (int off = 16; off; off >>= 1) part += shfl_u64(part, lane ^ off);
   if (lane == 0) s_red[warp] = part;
   __syncthreads();
-  uint64_t running = 0;
+  uint64_t running = a.base_in ? *a.base_in : 0ull;
 #pragma unroll
   for (int w = 0; w < kJoinWarps; ++w) running += s_red[w];
 
@@ -554,7 +555,8 @@ static int sm_count(int device) {
 int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_qgroup,
                 const uint32_t* d_qlow, const uint32_t* d_qhigh, uint64_t* d_offsets,
                 uint64_t pair_capacity, uint32_t* d_hit_query, uint32_t* d_hit_target,
-                uint64_t* d_total, uint8_t* d_any, uint32_t query_id_base, cudaStream_t stream) {
+                uint64_t* d_total, uint8_t* d_any, uint32_t query_id_base, cudaStream_t stream,
+                const uint64_t* d_offset_base) {
   if (n_q > 0xfffffffeull) { set_error("query batch exceeds 2^32-2 queries"); return BCU_E_LIMIT; }
   if (mode < 0 || mode > 3) { set_error("bad join mode %d", mode); return BCU_E_INVALID; }
   const bool prefix = (mode == kModeCount || mode == kModeFused);
@@ -591,6 +593,7 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
   a.st_lb = nullptr;
   a.st_w = nullptr;
   a.cta_total = nullptr;
+  a.base_in = d_offset_base;
   const uint64_t n_tiles = (n_q + kCtaTile - 1) / kCtaTile;
   const uint64_t cta_budget = (uint64_t)sm_count(ix->device) * kJoinMinBlocks * 2;  // two waves of CTAs
   if (!prefix) {

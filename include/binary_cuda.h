@@ -92,13 +92,15 @@ int bcu_query_count(const bcu_index* index, uint64_t n_q, const uint32_t* qgroup
 int bcu_query_scatter(const bcu_index* index, uint64_t n_q, const uint32_t* qgroup,
                       const uint32_t* qlow, const uint32_t* qhigh, const uint64_t* offsets,
                       uint32_t* hit_query, uint32_t* hit_target);
-/* One call, one pass over the queries: count, prefix-sum and scatter fused in one kernel, chunks
- * pipelined over copy/compute streams. pair_capacity = entries available in hit_query/hit_target;
- * if the join produces more, returns BCU_E_CAPACITY with *total = required entries (offsets are
- * complete and valid in that case, pairs are not). */
+/* One call for the whole join (what the sv2nl loop switches to): the batch is cut into chunks that are
+ * pipelined over copy-in / compute / copy-out streams. pair_capacity = entries available in
+ * hit_query/hit_target; if the join produces more, returns BCU_E_CAPACITY with *total = required entries
+ * (offsets are complete and valid in that case, pairs are not). Staging buffers are cached per host
+ * thread; bcu_trim() releases them. */
 int bcu_join(const bcu_index* index, uint64_t n_q, const uint32_t* qgroup, const uint32_t* qlow,
              const uint32_t* qhigh, uint64_t* offsets, uint64_t pair_capacity, uint32_t* hit_query,
              uint32_t* hit_target, uint64_t* total);
+int bcu_trim(void);
 /* any[i] = 1 iff query i overlaps at least one target (shape-independent part of find_overlap). */
 int bcu_query_any(const bcu_index* index, uint64_t n_q, const uint32_t* qgroup,
                   const uint32_t* qlow, const uint32_t* qhigh, uint8_t* any);
@@ -112,9 +114,9 @@ int bcu_query_scatter_dev(const bcu_index* index, uint64_t n_q, const uint32_t* 
                           const uint32_t* d_qlow, const uint32_t* d_qhigh,
                           const uint64_t* d_offsets, uint32_t* d_hit_query, uint32_t* d_hit_target,
                           void* stream);
-/* Fused single pass. d_total: u64[1] on device, receives the number of pairs the join has (also
- * when it exceeds pair_capacity, in which case pairs beyond the capacity are not written).
- * query_id_base is added to every emitted query id, offset_base to every offset (for sharding). */
+/* Count + prefix sum + scatter (probe and emit kernels back to back). d_total: u64[1] on device,
+ * receives the number of pairs the join has (also when it exceeds pair_capacity, in which case pairs
+ * beyond the capacity are not written). query_id_base is added to every emitted query id (sharding). */
 int bcu_join_dev(const bcu_index* index, uint64_t n_q, const uint32_t* d_qgroup,
                  const uint32_t* d_qlow, const uint32_t* d_qhigh, uint64_t* d_offsets,
                  uint64_t pair_capacity, uint32_t* d_hit_query, uint32_t* d_hit_target,
