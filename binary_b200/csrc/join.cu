@@ -38,8 +38,17 @@ constexpr int kJoinWarps = kJoinThreads / 32;
 constexpr int kQPT = 4;                            // queries per lane: one 128-bit load per input column
 constexpr int kWarpTile = 32 * kQPT;               // 128 queries per warp step
 constexpr int kCtaTile = kJoinWarps * kWarpTile;   // 1024 queries per CTA step
+#ifndef BCU_PROBE_MB
+#define BCU_PROBE_MB 4
+#endif
+#ifndef BCU_EMIT_MB
+#define BCU_EMIT_MB 4
+#endif
 constexpr int kJoinMinBlocks = 4;
-constexpr uint32_t kScalarMax = 16;                // longer candidate ranges go to the warp-cooperative path
+constexpr int kProbeMinBlocks = BCU_PROBE_MB;
+constexpr int kEmitMinBlocks = BCU_EMIT_MB;
+constexpr uint32_t kScalarMax = 31;                // longer candidate ranges go to the warp-cooperative path
+                                                   // (31 = hit-mask bits left beside the flag bit of the state word)
 constexpr int kStage = 256;                        // staged hits per warp and round
 constexpr int kDirectGroups = 1024;                // group values below this use a direct map
 constexpr uint32_t kBigFlag = 0x80000000u;         // state word: bit 31 = long range, low bits = hit count
@@ -278,19 +287,23 @@ __device__ __forceinline__ void emit_short(const JoinArgs& a, StageBuffers& st, 
 #pragma unroll
     for (int j = 0; j < kQPT; ++j) {
       uint32_t m = mask[j];
-      uint64_t pos = off[j];
-      while (m) {
-        const uint32_t k = __ffs(m) - 1;
-        m &= m - 1;
-        const uint32_t s = slot - r0;  // wraps below the window: caught by the unsigned compare
-        if (s < (uint32_t)kStage) {
-          st.val[warp][s] = lb[j] + k;
-          st.pos[warp][s] = pos;
-          st.qi[warp][s] = (uint8_t)(lane * kQPT + j);
+      const uint32_t n_j = __popc(m);
+      if (slot + n_j > r0 && slot < r0 + kStage) {  // this query has hits inside the round's window
+        uint64_t pos = off[j];
+        uint32_t s = slot - r0;  // wraps below the window: caught by the unsigned compare
+        while (m) {
+          const uint32_t k = __ffs(m) - 1;
+          m &= m - 1;
+          if (s < (uint32_t)kStage) {
+            st.val[warp][s] = lb[j] + k;
+            st.pos[warp][s] = pos;
+            st.qi[warp][s] = (uint8_t)(lane * kQPT + j);
+          }
+          ++s;
+          ++pos;
         }
-        ++slot;
-        ++pos;
       }
+      slot += n_j;
     }
     __syncwarp();
     const uint32_t n_here = min((uint32_t)kStage, staged_total - r0);
@@ -307,7 +320,7 @@ __device__ __forceinline__ void emit_short(const JoinArgs& a, StageBuffers& st, 
 
 // ---------------------------------------------------------------------------------------------------
 // K3: probe. No barriers inside the chunk loop.
-__global__ void __launch_bounds__(kJoinThreads, kJoinMinBlocks) probe_kernel(const JoinArgs a) {
+__global__ void __launch_bounds__(kJoinThreads, kProbeMinBlocks) probe_kernel(const JoinArgs a) {
   __shared__ GroupTables tb;
   __shared__ uint64_t s_warp_total[kJoinWarps];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -365,7 +378,7 @@ __global__ void __launch_bounds__(kJoinThreads, kJoinMinBlocks) probe_kernel(con
 // ---------------------------------------------------------------------------------------------------
 // K4: prefix sum + scatter. One barrier per 1024 queries, no waiting on other CTAs.
 template <bool EMIT>
-__global__ void __launch_bounds__(kJoinThreads, kJoinMinBlocks) emit_kernel(const JoinArgs a) {
+__global__ void __launch_bounds__(kJoinThreads, kEmitMinBlocks) emit_kernel(const JoinArgs a) {
   __shared__ GroupTables tb;
   __shared__ StageBuffers st;
   __shared__ uint64_t s_warp_total[2][kJoinWarps];
