@@ -188,6 +188,7 @@ def run_ours(args):
     w, n_t, n_q = workload_for(args)
     tg, tl, th = w.targets(n_t)
     # shard = this rank's contiguous query range of the (counter-based) stream; no data-path collective
+    # (binary_b200.sharding.shard_range over world*n_q queries: rank r gets [r*n_q, (r+1)*n_q))
     q_start = rank * n_q
     qg, ql, qh = w.queries(q_start, n_q)
 

@@ -186,3 +186,39 @@ def test_full_size_configs_count_and_hash(port_oracle, name):
     ix.count_dev(half, d_ql.data_ptr(), d_qh.data_ptr(), d_off3.data_ptr(), d_qg.data_ptr(), stream)
     torch.cuda.synchronize()
     assert torch.equal(d_off3, d_off[: half + 1])
+
+
+def test_sharded_join_on_gpu(port_oracle):
+    """The N>1 path on one GPU: 3 emulated ranks run their query ranges one after the other with
+    query_id_base (as bench.py's ranks do), pieces are concatenated -- must equal the unsharded oracle."""
+    import torch
+    from binary_b200.sharding import ShardedJoin, assemble
+    c = random_case(55, n_t=30000, n_q=20011, n_groups=5, dup_frac=0.05, long_frac=0.001)
+    dev = torch.device("cuda:0")
+    ix = DeviceIndex.build(c["tl"], c["th"], c["tg"])
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def gpu_join(ql, qh, qg, qid_base):
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).to(dev)
+        d_ql, d_qh, d_qg = t(ql), t(qh), t(qg)
+        n = ql.size
+        d_off = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        ix.count_dev(n, d_ql.data_ptr(), d_qh.data_ptr(), d_off.data_ptr(), d_qg.data_ptr(), stream)
+        total = int(d_off[-1].item())
+        d_hq = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        d_ht = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        d_total = torch.zeros(1, dtype=torch.int64, device=dev)
+        ix.join_dev(n, d_ql.data_ptr(), d_qh.data_ptr(), d_off.data_ptr(), total, d_hq.data_ptr(), d_ht.data_ptr(),
+                    d_total.data_ptr(), d_qg.data_ptr(), qid_base, stream)
+        torch.cuda.synchronize()
+        assert int(d_total.item()) == total
+        return (d_off.cpu().numpy().view(np.uint64), d_hq[:total].cpu().numpy().view(np.uint32),
+                d_ht[:total].cpu().numpy().view(np.uint32))
+
+    pieces = [ShardedJoin(gpu_join, r, 3).run(c["ql"], c["qh"], c["qg"]) for r in (2, 0, 1)]
+    off, hq, ht = assemble(pieces)
+    f = port_oracle.build(c["tl"], c["th"], c["tg"])
+    want_off, want_tid = f.query_sorted_pairs(c["ql"], c["qh"], c["qg"], threads=4)
+    assert np.array_equal(off, want_off)
+    assert np.array_equal(hq, np.repeat(np.arange(c["ql"].size, dtype=np.uint32), np.diff(want_off).astype(np.int64)))
+    assert np.array_equal(canonical(off, ht)[1], want_tid)
