@@ -88,9 +88,9 @@ struct GroupTables {
 };
 
 struct StageBuffers {
-  uint64_t pos[kJoinWarps][kStage];  // output position of each staged hit (relative to the warp's base)
-  uint32_t val[kJoinWarps][kStage];  // sorted-row index of the hit
-  uint8_t qi[kJoinWarps][kStage];    // query index inside the warp's 128
+  uint64_t pos[kJoinWarps][kStage];  // output position of each staged hit relative to the warp's base
+                                     // (only used when long ranges sit between the short ones)
+  uint2 vq[kJoinWarps][kStage];      // {sorted-row index of the hit, query index inside the warp's 128}
 };
 
 // Read-only 128/64-bit loads as ONE instruction. Written as PTX because the compiler otherwise may split
@@ -270,6 +270,8 @@ __device__ __forceinline__ uint32_t warp_scan_range(const JoinArgs& a, uint32_t 
 // K4 scatter, short ranges of one warp (128 queries): stage each hit's row at its rank among the warp's
 // short-range hits, then gather rows -> target ids with independent loads and write to consecutive
 // addresses. off[j] = output position of query j's first hit, relative to `base`.
+// GAPS = false: the warp has no long range, so a hit's output position IS its rank (no position array).
+template <bool GAPS>
 __device__ __forceinline__ void emit_short(const JoinArgs& a, StageBuffers& st, int warp, int lane,
                                            const uint32_t (&mask)[kQPT], const uint32_t (&lb)[kQPT],
                                            const uint64_t (&off)[kQPT], uint64_t base, uint32_t qid0) {
@@ -288,19 +290,24 @@ __device__ __forceinline__ void emit_short(const JoinArgs& a, StageBuffers& st, 
     for (int j = 0; j < kQPT; ++j) {
       uint32_t m = mask[j];
       const uint32_t n_j = __popc(m);
-      if (slot + n_j > r0 && slot < r0 + kStage) {  // this query has hits inside the round's window
-        uint64_t pos = off[j];
+      if (n_j && slot + n_j > r0 && slot < r0 + kStage) {  // this query has hits inside the round's window
+        const uint32_t qi = (uint32_t)(lane * kQPT + j);
         uint32_t s = slot - r0;  // wraps below the window: caught by the unsigned compare
+        uint64_t pos = off[j];
+        // most queries have exactly one hit: handle it without the loop
+        if (s < (uint32_t)kStage) {
+          st.vq[warp][s] = make_uint2(lb[j] + (__ffs(m) - 1), qi);
+          if (GAPS) st.pos[warp][s] = pos;
+        }
+        m &= m - 1;
         while (m) {
-          const uint32_t k = __ffs(m) - 1;
-          m &= m - 1;
-          if (s < (uint32_t)kStage) {
-            st.val[warp][s] = lb[j] + k;
-            st.pos[warp][s] = pos;
-            st.qi[warp][s] = (uint8_t)(lane * kQPT + j);
-          }
           ++s;
           ++pos;
+          if (s < (uint32_t)kStage) {
+            st.vq[warp][s] = make_uint2(lb[j] + (__ffs(m) - 1), qi);
+            if (GAPS) st.pos[warp][s] = pos;
+          }
+          m &= m - 1;
         }
       }
       slot += n_j;
@@ -308,10 +315,11 @@ __device__ __forceinline__ void emit_short(const JoinArgs& a, StageBuffers& st, 
     __syncwarp();
     const uint32_t n_here = min((uint32_t)kStage, staged_total - r0);
     for (uint32_t s = lane; s < n_here; s += 32) {
-      const uint64_t pos = base + st.pos[warp][s];
+      const uint2 v = st.vq[warp][s];
+      const uint64_t pos = base + (GAPS ? st.pos[warp][s] : (uint64_t)(r0 + s));
       if (pos < a.capacity) {
-        a.hit_target[pos] = a.ids[st.val[warp][s]];
-        a.hit_query[pos] = qid0 + st.qi[warp][s];
+        a.hit_target[pos] = a.ids[v.x];
+        a.hit_query[pos] = qid0 + v.y;
       }
     }
     __syncwarp();
@@ -469,8 +477,10 @@ __global__ void __launch_bounds__(kJoinThreads, kEmitMinBlocks) emit_kernel(cons
     if (!EMIT) continue;
 
     // ---- scatter ------------------------------------------------------------------------------------
-    emit_short(a, st, warp, lane, mask, lb, off, warp_base, a.qid_base + w0);
-    if (__any_sync(0xffffffffu, lane_big)) {
+    const bool warp_big = __any_sync(0xffffffffu, lane_big);
+    if (warp_big) emit_short<true>(a, st, warp, lane, mask, lb, off, warp_base, a.qid_base + w0);
+    else emit_short<false>(a, st, warp, lane, mask, lb, off, warp_base, a.qid_base + w0);
+    if (warp_big) {
       uint32_t ql[kQPT], qh[kQPT], qg[kQPT];
       load_queries(a, q0, ql, qh, qg);
 #pragma unroll
@@ -531,7 +541,7 @@ __global__ void __launch_bounds__(kJoinThreads, kJoinMinBlocks) direct_kernel(co
     uint64_t off[kQPT];
 #pragma unroll
     for (int j = 0; j < kQPT; ++j) off[j] = (q0 + j < a.n_q) ? a.offsets[q0 + j] : 0ull;
-    emit_short(a, st, warp, lane, mask, lb, off, 0, a.qid_base + w0);
+    emit_short<true>(a, st, warp, lane, mask, lb, off, 0, a.qid_base + w0);
 #pragma unroll
     for (int j = 0; j < kQPT; ++j) {
       unsigned big = __ballot_sync(0xffffffffu, len[j] > kScalarMax);
