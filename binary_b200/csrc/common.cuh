@@ -75,7 +75,8 @@ struct bcu_index {
   uint64_t n_bins = 0;
   uint64_t bytes = 0;
   uint2* d_lowhigh = nullptr;        // [n+2] {low, high} of the targets sorted by (group, low, id)
-  uint32_t* d_id = nullptr;          // [n]   insertion ordinal of each sorted row
+  uint32_t* d_high = nullptr;        // [n+4] `high` of the same rows as a plain column (long-range scans)
+  uint32_t* d_id = nullptr;          // [n+4] insertion ordinal of each sorted row
   uint32_t* d_runmax = nullptr;      // [n]   running max of high inside the group (max-end array)
   bcu::GroupDesc* d_groups = nullptr;  // [n_groups]
   uint2* d_dir = nullptr;            // [n_bins] entry b = {first row with runmax >= b*W, first row with low >= (b+1)*W}

@@ -120,6 +120,7 @@ static double env_double(const char* name, double dflt) {
 static void free_index_members(bcu_index* ix) {
   cudaFree(ix->d_lowhigh);
   cudaFree(ix->d_id);
+  cudaFree(ix->d_high);
   cudaFree(ix->d_runmax);
   cudaFree(ix->d_groups);
   cudaFree(ix->d_dir);
@@ -162,12 +163,11 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
   if (n == 0) return BCU_OK;
   TempBuffers tmp(stream);
   uint64_t *keys_a, *keys_b;
-  uint32_t *vals_a, *vals_b, *high_sorted, *head_rows, *counters;
+  uint32_t *vals_a, *vals_b, *head_rows, *counters;
   BCU_CUDA(tmp.alloc(&keys_a, n));
   BCU_CUDA(tmp.alloc(&keys_b, n));
   BCU_CUDA(tmp.alloc(&vals_a, n));
   BCU_CUDA(tmp.alloc(&vals_b, n));
-  BCU_CUDA(tmp.alloc(&high_sorted, n));
   BCU_CUDA(tmp.alloc(&head_rows, n));
   BCU_CUDA(tmp.alloc(&counters, 4));  // [0..1] varying bits (u64), [2] n_heads
   BCU_CUDA(cudaMemsetAsync(counters, 0, 16, stream));
@@ -187,14 +187,17 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
 
   BCU_CUDA(cudaMalloc((void**)&ix->d_lowhigh, (n + 2) * sizeof(uint2)));  // +pad: join.cu reads row pairs
   BCU_CUDA(cudaMemsetAsync(ix->d_lowhigh + n, 0, 2 * sizeof(uint2), stream));
-  BCU_CUDA(cudaMalloc((void**)&ix->d_id, n * 4));
+  BCU_CUDA(cudaMalloc((void**)&ix->d_id, (n + 4) * 4));  // +pad: 128-bit loads of 4 rows
+  BCU_CUDA(cudaMalloc((void**)&ix->d_high, (n + 4) * 4));
+  BCU_CUDA(cudaMemsetAsync(ix->d_id + n, 0, 16, stream));
+  BCU_CUDA(cudaMemsetAsync(ix->d_high + n, 0, 16, stream));
   BCU_CUDA(cudaMalloc((void**)&ix->d_runmax, n * 4));
-  ix->bytes += n * 16;
+  ix->bytes += n * 20;
   const unsigned grid_rows = (unsigned)((n + kThreads - 1) / kThreads);
   gather_rows_kernel<<<grid_rows, kThreads, 0, stream>>>(keys, vals, d_high, n, ix->d_lowhigh, ix->d_id,
-                                                        high_sorted, head_rows, counters + 2);
+                                                        ix->d_high, head_rows, counters + 2);
   BCU_LAUNCHED();
-  BCU_TRY(segmented_running_max(keys, high_sorted, ix->d_runmax, n, stream));
+  BCU_TRY(segmented_running_max(keys, ix->d_high, ix->d_runmax, n, stream));
 
   // ---- groups: sort the head rows on the host (few), probe value / max coordinate per group ----
   uint32_t n_groups = 0;

@@ -20,7 +20,8 @@
 //                            on each. Short ranges: by the owning lane, its 4 queries interleaved so
 //                            their loads overlap, result = a hit bitmask. Long ranges: by the whole warp,
 //                            128 rows per trip with 128-bit loads.
-//                  Output: per query 8 bytes of state {lb, hit mask | count} + one hit total per CTA.
+//                  Output: per query 8 bytes of state {lb, hit mask | count} (+ the exact end row of long
+//                  ranges) + one hit total per CTA.
 //   emit_kernel    K4. Same chunks. A CTA first sums the totals of the chunks before its own (its
 //                  global base), then walks its chunk 1024 queries at a time: counts from the state ->
 //                  warp scan + one barrier -> u64 CSR offsets, in query order; short-range hits are staged
@@ -55,6 +56,7 @@ constexpr uint32_t kBigFlag = 0x80000000u;         // state word: bit 31 = long 
 
 struct JoinArgs {
   const uint2* __restrict__ lowhigh;
+  const uint32_t* __restrict__ high;  // SoA copy of lowhigh[].y, padded: the long-range path streams it
   const uint32_t* __restrict__ ids;
   const uint2* __restrict__ dir;
   const GroupDesc* __restrict__ groups;
@@ -76,6 +78,7 @@ struct JoinArgs {
   uint32_t qid_base;
   uint32_t* st_lb;      // [n_q rounded up to kCtaTile] probe state: first candidate row
   uint32_t* st_w;       // [same] probe state: hit bitmask, or kBigFlag | hit count
+  uint32_t* st_ub;      // [same] probe state of LONG ranges only: exact end row (untouched otherwise)
   uint64_t* cta_total;  // [gridDim.x] hits per chunk
   const uint64_t* base_in;  // optional: offset of the batch's first pair (chunked host pipeline)
 };
@@ -221,50 +224,184 @@ __device__ __forceinline__ void scan_short(const JoinArgs& a, const uint32_t (&q
   }
 }
 
-// K3 step 2, long ranges: warp-cooperative scan of the rows [blb, bub): every lane takes two adjacent
-// rows per 128-bit load and keeps two loads in flight (128 rows per trip). `lowhigh` is 16-byte aligned
-// and padded by two rows, so the pair that straddles `bub` may be read.
-// EMIT = false: returns the hit count (in every lane).
-// EMIT = true : writes (qid, id) of the hits to consecutive slots from `base`, in row order.
+// K3/K4, long ranges. A long range [lb, ub) is first trimmed to the EXACT upper bound by its owning lane
+// (the directory's ub is at most about one bin of rows too far; walking back over `low` costs ~1 load), so
+// that every remaining row satisfies t.low <= q.high and only t.high >= q.low is left to test. The warp then
+// streams the SoA column `high` (4 B per row instead of 8) with 128-bit loads, 4 adjacent rows per lane,
+// and works on TWO ranges at a time so their loads overlap. When emitting, the matching `id` column is
+// loaded alongside (no dependent gather), hits are ranked by a warp shuffle scan and written to consecutive
+// slots; the query-id column of a long range is one value and is filled with coalesced stores.
+struct LongCtx {  // what the long-range path needs, passed BY VALUE into the out-of-line function so
+                  // that the callers' per-query arrays stay in registers on the (common) short path
+  const uint32_t* high;
+  const uint32_t* ids;
+  uint32_t* hit_target;
+  uint32_t* hit_query;
+  uint64_t capacity;
+};
+
+struct LongRange {
+  uint32_t lb, ub, ql;  // rows [lb, ub), query low
+  uint32_t cnt;         // EMIT: number of hits (from the probe state)
+  uint32_t qid;
+  uint64_t base;        // EMIT: output position of the first hit
+};
+
+__device__ __forceinline__ uint32_t exact_upper_bound(const JoinArgs& a, uint32_t lb, uint32_t len,
+                                                      uint32_t qh) {
+  uint32_t u = lb + len;
+  while (u > lb && a.lowhigh[u - 1].x > qh) --u;
+  return u;
+}
+
+// bits k = 0..3: row r+k lies inside [lb, ub)
+__device__ __forceinline__ uint32_t rows_in_range(uint32_t r, uint32_t lb, uint32_t ub) {
+  const uint32_t n_hi = ub > r ? min(ub - r, 4u) : 0u;
+  const uint32_t n_lo = lb > r ? min(lb - r, 4u) : 0u;
+  return ((1u << n_hi) - 1u) & ~((1u << n_lo) - 1u);
+}
+__device__ __forceinline__ uint32_t reaches(uint32_t ql, const uint4& h) {
+  return (uint32_t)(ql <= h.x) | ((uint32_t)(ql <= h.y) << 1) | ((uint32_t)(ql <= h.z) << 2) |
+         ((uint32_t)(ql <= h.w) << 3);
+}
+
 template <bool EMIT>
-__device__ __forceinline__ uint32_t warp_scan_range(const JoinArgs& a, uint32_t blb, uint32_t bub,
-                                                    uint32_t ql, uint32_t qh, int lane, uint64_t base,
-                                                    uint32_t qid) {
-  const uint4* pairs = reinterpret_cast<const uint4*>(a.lowhigh);
-  const uint32_t p_end = (bub + 1u) >> 1;
-  const unsigned lt = (1u << lane) - 1u;
-  uint32_t c = 0;
-  for (uint32_t p0 = blb >> 1; p0 < p_end; p0 += 64) {
-    const uint32_t pa = p0 + lane, pb = pa + 32;
-    const bool va = pa < p_end, vb = pb < p_end;
-    uint4 ta = make_uint4(0, 0, 0, 0), tb = make_uint4(0, 0, 0, 0);
-    if (va) ta = ldg_u4(pairs + pa);
-    if (vb) tb = ldg_u4(pairs + pb);
-    const uint32_t ra = pa * 2, rb = pb * 2;
-    const bool h0 = va && ra >= blb && ra < bub && overlaps(ql, qh, ta.x, ta.y);
-    const bool h1 = va && ra + 1 >= blb && ra + 1 < bub && overlaps(ql, qh, ta.z, ta.w);
-    const bool h2 = vb && rb >= blb && rb < bub && overlaps(ql, qh, tb.x, tb.y);
-    const bool h3 = vb && rb + 1 >= blb && rb + 1 < bub && overlaps(ql, qh, tb.z, tb.w);
-    if (!EMIT) {
-      c += (uint32_t)h0 + h1 + h2 + h3;
-    } else {
-      const unsigned b0 = __ballot_sync(0xffffffffu, h0), b1 = __ballot_sync(0xffffffffu, h1);
-      const unsigned b2 = __ballot_sync(0xffffffffu, h2), b3 = __ballot_sync(0xffffffffu, h3);
-      const uint32_t n_a = __popc(b0) + __popc(b1);
-      uint64_t pos = base + __popc(b0 & lt) + __popc(b1 & lt);
-      if (h0) { if (pos < a.capacity) { a.hit_target[pos] = a.ids[ra]; a.hit_query[pos] = qid; } ++pos; }
-      if (h1) { if (pos < a.capacity) { a.hit_target[pos] = a.ids[ra + 1]; a.hit_query[pos] = qid; } }
-      pos = base + n_a + __popc(b2 & lt) + __popc(b3 & lt);
-      if (h2) { if (pos < a.capacity) { a.hit_target[pos] = a.ids[rb]; a.hit_query[pos] = qid; } ++pos; }
-      if (h3) { if (pos < a.capacity) { a.hit_target[pos] = a.ids[rb + 1]; a.hit_query[pos] = qid; } }
-      base += n_a + __popc(b2) + __popc(b3);
+__device__ __forceinline__ void scan_two_long(const LongCtx& c, int lane, const LongRange& A,
+                                              const LongRange& B, bool has_b, uint32_t& cnt_a,
+                                              uint32_t& cnt_b) {
+  const uint4* high4 = reinterpret_cast<const uint4*>(c.high);
+  const uint4* id4 = reinterpret_cast<const uint4*>(c.ids);
+  uint32_t ca = 0, cb = 0;  // COUNT: lane-local hit counts; EMIT: hits of the range written so far
+  uint32_t ra = (A.lb & ~3u) + 4u * lane, rb = (B.lb & ~3u) + 4u * lane;
+  const uint32_t end_a = A.ub, end_b = has_b ? B.ub : 0u;
+  // EMIT: 32-bit ranks against a per-range pointer; `lim` = slots of the range that fit the capacity
+  uint32_t* out_a = c.hit_target + A.base;
+  uint32_t* out_b = c.hit_target + B.base;
+  const uint32_t lim_a = c.capacity > A.base ? (uint32_t)min(c.capacity - A.base, (uint64_t)0xffffffffu) : 0u;
+  const uint32_t lim_b = c.capacity > B.base ? (uint32_t)min(c.capacity - B.base, (uint64_t)0xffffffffu) : 0u;
+  while (((ra - 4u * lane) < end_a) | ((rb - 4u * lane) < end_b)) {  // warp-uniform (lane 0's row)
+    const bool va = ra < end_a, vb = rb < end_b;
+    uint4 ha = make_uint4(0, 0, 0, 0), hb = make_uint4(0, 0, 0, 0), ia, ib;
+    if (va) ha = ldg_u4(high4 + (ra >> 2));
+    if (vb) hb = ldg_u4(high4 + (rb >> 2));
+    if (EMIT) {
+      ia = ib = make_uint4(0, 0, 0, 0);
+      if (va) ia = ldg_u4(id4 + (ra >> 2));
+      if (vb) ib = ldg_u4(id4 + (rb >> 2));
     }
+    const uint32_t ma = rows_in_range(ra, A.lb, end_a) & reaches(A.ql, ha);
+    const uint32_t mb = rows_in_range(rb, B.lb, end_b) & reaches(B.ql, hb);
+    if (!EMIT) {
+      ca += __popc(ma);
+      cb += __popc(mb);
+    } else {
+      // both streams' lane counts packed in one register: one shuffle scan ranks both
+      const uint32_t c2 = __popc(ma) | (__popc(mb) << 16);
+      uint32_t incl = c2;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+      const uint32_t excl = incl - c2;
+      uint32_t p = ca + (excl & 0xffffu);
+      if ((ma & 1u) && p < lim_a) out_a[p] = ia.x;
+      p += ma & 1u;
+      if ((ma & 2u) && p < lim_a) out_a[p] = ia.y;
+      p += (ma >> 1) & 1u;
+      if ((ma & 4u) && p < lim_a) out_a[p] = ia.z;
+      p += (ma >> 2) & 1u;
+      if ((ma & 8u) && p < lim_a) out_a[p] = ia.w;
+      p = cb + (excl >> 16);
+      if ((mb & 1u) && p < lim_b) out_b[p] = ib.x;
+      p += mb & 1u;
+      if ((mb & 2u) && p < lim_b) out_b[p] = ib.y;
+      p += (mb >> 1) & 1u;
+      if ((mb & 4u) && p < lim_b) out_b[p] = ib.z;
+      p += (mb >> 2) & 1u;
+      if ((mb & 8u) && p < lim_b) out_b[p] = ib.w;
+      ca += tot & 0xffffu;
+      cb += tot >> 16;
+    }
+    ra += 128;
+    rb += 128;
   }
   if (!EMIT) {
 #pragma unroll
-    for (int off = 16; off; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+    for (int off = 16; off; off >>= 1) {
+      ca += __shfl_xor_sync(0xffffffffu, ca, off);
+      cb += __shfl_xor_sync(0xffffffffu, cb, off);
+    }
+    cnt_a = ca;
+    cnt_b = cb;
+  } else {
+    // query-id column: one value per range, coalesced fill
+    uint32_t* qa = c.hit_query + A.base;
+    const uint32_t na = min(A.cnt, lim_a);
+    for (uint32_t k = lane; k < na; k += 32) qa[k] = A.qid;
+    if (has_b) {
+      uint32_t* qb = c.hit_query + B.base;
+      const uint32_t nb = min(B.cnt, lim_b);
+      for (uint32_t k = lane; k < nb; k += 32) qb[k] = B.qid;
+    }
   }
+}
+
+// All long ranges of the warp's 128 queries, two at a time. Lane-local inputs per query j (packed in
+// vectors, by value): bit j of `bigbits`, the exact row range [lb.j, ub.j), ql.j; EMIT also needs cnt.j
+// (from the probe) and the absolute output position pos.j. COUNT returns cnt.j of the long ranges.
+template <bool EMIT>
+__device__ __noinline__ uint4 long_ranges(LongCtx c, int lane, uint32_t bigbits, uint4 lb4, uint4 ub4,
+                                          uint4 ql4, uint4 cnt4, uint64_t pos_0, uint64_t pos_1,
+                                          uint64_t pos_2, uint64_t pos_3, uint32_t qid0) {
+  const uint32_t lb[kQPT] = {lb4.x, lb4.y, lb4.z, lb4.w};
+  const uint32_t ub[kQPT] = {ub4.x, ub4.y, ub4.z, ub4.w};
+  const uint32_t ql[kQPT] = {ql4.x, ql4.y, ql4.z, ql4.w};
+  uint32_t cnt[kQPT] = {cnt4.x, cnt4.y, cnt4.z, cnt4.w};
+  const uint64_t pos0[kQPT] = {pos_0, pos_1, pos_2, pos_3};
+#pragma unroll
+  for (int j = 0; j < kQPT; ++j) {
+    unsigned todo = __ballot_sync(0xffffffffu, (bigbits >> j) & 1u);
+    while (todo) {
+      const int sa = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const bool has_b = todo != 0;
+      const int sb = has_b ? __ffs(todo) - 1 : sa;
+      if (has_b) todo &= todo - 1;
+      LongRange A, B;
+      A.lb = __shfl_sync(0xffffffffu, lb[j], sa); B.lb = __shfl_sync(0xffffffffu, lb[j], sb);
+      A.ub = __shfl_sync(0xffffffffu, ub[j], sa); B.ub = __shfl_sync(0xffffffffu, ub[j], sb);
+      A.ql = __shfl_sync(0xffffffffu, ql[j], sa); B.ql = __shfl_sync(0xffffffffu, ql[j], sb);
+      A.qid = qid0 + (uint32_t)sa * kQPT + j;       B.qid = qid0 + (uint32_t)sb * kQPT + j;
+      A.cnt = B.cnt = 0;
+      A.base = B.base = 0;
+      if (EMIT) {
+        A.cnt = __shfl_sync(0xffffffffu, cnt[j], sa); B.cnt = __shfl_sync(0xffffffffu, cnt[j], sb);
+        A.base = shfl_u64(pos0[j], sa);               B.base = shfl_u64(pos0[j], sb);
+      }
+      uint32_t ca = 0, cb = 0;
+      scan_two_long<EMIT>(c, lane, A, B, has_b, ca, cb);
+      if (!EMIT) {
+        if (lane == sa) cnt[j] = ca;
+        if (has_b && lane == sb) cnt[j] = cb;
+      }
+    }
+  }
+  return make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]);
+}
+
+__device__ __forceinline__ LongCtx long_ctx(const JoinArgs& a) {
+  LongCtx c;
+  c.high = a.high;
+  c.ids = a.ids;
+  c.hit_target = a.hit_target;
+  c.hit_query = a.hit_query;
+  c.capacity = a.capacity;
   return c;
+}
+__device__ __forceinline__ uint32_t pack_bits(const bool (&b)[kQPT]) {
+  return (uint32_t)b[0] | ((uint32_t)b[1] << 1) | ((uint32_t)b[2] << 2) | ((uint32_t)b[3] << 3);
 }
 
 // K4 scatter, short ranges of one warp (128 queries): stage each hit's row at its rank among the warp's
@@ -352,20 +489,28 @@ __global__ void __launch_bounds__(kJoinThreads, kProbeMinBlocks) probe_kernel(co
 #pragma unroll
     for (int j = 0; j < kQPT; ++j) query_bounds(a, tb, q0 + j < a.n_q, ql[j], qh[j], qg[j], lb[j], len[j]);
     scan_short(a, ql, qh, lb, len, w);
+    bool big[kQPT];
+    uint32_t ub[kQPT];
+    bool lane_big = false;
 #pragma unroll
     for (int j = 0; j < kQPT; ++j) {
       acc += __popc(w[j]);
-      unsigned big = __ballot_sync(0xffffffffu, len[j] > kScalarMax);
-      while (big) {
-        const int src = __ffs(big) - 1;
-        big &= big - 1;
-        const uint32_t blb = __shfl_sync(0xffffffffu, lb[j], src);
-        const uint32_t bub = blb + __shfl_sync(0xffffffffu, len[j], src);
-        const uint32_t bql = __shfl_sync(0xffffffffu, ql[j], src);
-        const uint32_t bqh = __shfl_sync(0xffffffffu, qh[j], src);
-        const uint32_t c = warp_scan_range<false>(a, blb, bub, bql, bqh, lane, 0, 0);
-        if (lane == src) { w[j] = kBigFlag | c; acc += c; }
-      }
+      big[j] = len[j] > kScalarMax;
+      lane_big |= big[j];
+      ub[j] = lb[j] + len[j];
+    }
+    if (__any_sync(0xffffffffu, lane_big)) {
+#pragma unroll
+      for (int j = 0; j < kQPT; ++j)
+        if (big[j]) ub[j] = exact_upper_bound(a, lb[j], len[j], qh[j]);
+      const uint4 c4 = long_ranges<false>(long_ctx(a), lane, pack_bits(big), make_uint4(lb[0], lb[1], lb[2], lb[3]),
+                                          make_uint4(ub[0], ub[1], ub[2], ub[3]),
+                                          make_uint4(ql[0], ql[1], ql[2], ql[3]), make_uint4(0, 0, 0, 0), 0, 0,
+                                          0, 0, 0);
+      const uint32_t cl[kQPT] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+      for (int j = 0; j < kQPT; ++j)
+        if (big[j]) { acc += cl[j]; w[j] = kBigFlag | cl[j]; a.st_ub[q0 + j] = ub[j]; }
     }
     // state: 8 bytes per query, 128-bit stores (the arrays are padded to a multiple of kCtaTile)
     *reinterpret_cast<uint4*>(a.st_lb + q0) = make_uint4(lb[0], lb[1], lb[2], lb[3]);
@@ -387,12 +532,10 @@ __global__ void __launch_bounds__(kJoinThreads, kProbeMinBlocks) probe_kernel(co
 // K4: prefix sum + scatter. One barrier per 1024 queries, no waiting on other CTAs.
 template <bool EMIT>
 __global__ void __launch_bounds__(kJoinThreads, kEmitMinBlocks) emit_kernel(const JoinArgs a) {
-  __shared__ GroupTables tb;
   __shared__ StageBuffers st;
   __shared__ uint64_t s_warp_total[2][kJoinWarps];
   __shared__ uint64_t s_red[kJoinWarps];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (EMIT) load_group_tables(a, tb);  // only the long-range re-scan needs them
 
   // global base of this chunk = hits of all chunks before it
   uint64_t part = 0;
@@ -422,6 +565,7 @@ __global__ void __launch_bounds__(kJoinThreads, kEmitMinBlocks) emit_kernel(cons
     }
   }
   int par = 0;
+  bool seen_big = false;
   for (uint64_t t0 = chunk_begin; t0 < chunk_end; t0 += kCtaTile, par ^= 1) {
     const uint32_t w0 = (uint32_t)t0 + (uint32_t)warp * kWarpTile;
     const uint32_t q0 = w0 + (uint32_t)lane * kQPT;
@@ -480,26 +624,37 @@ __global__ void __launch_bounds__(kJoinThreads, kEmitMinBlocks) emit_kernel(cons
     const bool warp_big = __any_sync(0xffffffffu, lane_big);
     if (warp_big) emit_short<true>(a, st, warp, lane, mask, lb, off, warp_base, a.qid_base + w0);
     else emit_short<false>(a, st, warp, lane, mask, lb, off, warp_base, a.qid_base + w0);
-    if (warp_big) {
-      uint32_t ql[kQPT], qh[kQPT], qg[kQPT];
-      load_queries(a, q0, ql, qh, qg);
+    seen_big |= warp_big;
+  }
+  if (!EMIT || !seen_big) return;
+
+  // ---- long ranges, in a second walk over the warp's steps ---------------------------------------------
+  // Kept out of the loop above so that its register needs (and the out-of-line call) do not spill into
+  // the hot short-range path. Everything comes from the probe state, the query column and the offsets
+  // this very thread wrote a moment ago.
+  for (uint64_t t0 = chunk_begin; t0 < chunk_end; t0 += kCtaTile) {
+    const uint32_t w0 = (uint32_t)t0 + (uint32_t)warp * kWarpTile;
+    const uint32_t q0 = w0 + (uint32_t)lane * kQPT;
+    uint4 w4 = make_uint4(0, 0, 0, 0);
+    if (t0 + (uint64_t)tid * kQPT < chunk_end) w4 = *reinterpret_cast<const uint4*>(a.st_w + q0);
+    const uint32_t w[kQPT] = {w4.x, w4.y, w4.z, w4.w};
+    if (!__any_sync(0xffffffffu, ((w4.x | w4.y | w4.z | w4.w) & kBigFlag) != 0)) continue;
+    uint32_t ql[kQPT], blb[kQPT], bub[kQPT], cnt[kQPT];
+    uint64_t pos[kQPT];
+    bool big[kQPT];
 #pragma unroll
-      for (int j = 0; j < kQPT; ++j) {
-        unsigned big = __ballot_sync(0xffffffffu, (w[j] & kBigFlag) != 0);
-        while (big) {
-          const int src = __ffs(big) - 1;
-          big &= big - 1;
-          uint32_t blb = 0, blen = 0;  // the owner recomputes its bounds (two cached 8-byte loads)
-          if (lane == src) query_bounds(a, tb, true, ql[j], qh[j], qg[j], blb, blen);
-          blb = __shfl_sync(0xffffffffu, blb, src);
-          const uint32_t bub = blb + __shfl_sync(0xffffffffu, blen, src);
-          const uint32_t bql = __shfl_sync(0xffffffffu, ql[j], src);
-          const uint32_t bqh = __shfl_sync(0xffffffffu, qh[j], src);
-          const uint64_t qbase = warp_base + shfl_u64(off[j], src);
-          warp_scan_range<true>(a, blb, bub, bql, bqh, lane, qbase, a.qid_base + w0 + (uint32_t)src * kQPT + j);
-        }
-      }
+    for (int j = 0; j < kQPT; ++j) {
+      big[j] = (w[j] & kBigFlag) != 0;
+      cnt[j] = w[j] & ~kBigFlag;
+      ql[j] = big[j] ? a.qlow[q0 + j] : 0u;
+      blb[j] = big[j] ? a.st_lb[q0 + j] : 0u;
+      bub[j] = big[j] ? a.st_ub[q0 + j] : 0u;
+      pos[j] = big[j] ? a.offsets[q0 + j] : 0ull;
     }
+    long_ranges<true>(long_ctx(a), lane, pack_bits(big), make_uint4(blb[0], blb[1], blb[2], blb[3]),
+                      make_uint4(bub[0], bub[1], bub[2], bub[3]), make_uint4(ql[0], ql[1], ql[2], ql[3]),
+                      make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]), pos[0], pos[1], pos[2], pos[3],
+                      a.qid_base + w0);
   }
 }
 
@@ -520,41 +675,46 @@ __global__ void __launch_bounds__(kJoinThreads, kJoinMinBlocks) direct_kernel(co
 #pragma unroll
     for (int j = 0; j < kQPT; ++j) query_bounds(a, tb, q0 + j < a.n_q, ql[j], qh[j], qg[j], lb[j], len[j]);
     scan_short(a, ql, qh, lb, len, mask);
-    if (MODE == kModeAny) {
+    bool big[kQPT];
+    uint32_t ub[kQPT], cnt[kQPT];
+    bool lane_big = false;
 #pragma unroll
-      for (int j = 0; j < kQPT; ++j) {
-        uint32_t c = mask[j];
-        unsigned big = __ballot_sync(0xffffffffu, len[j] > kScalarMax);
-        while (big) {
-          const int src = __ffs(big) - 1;
-          big &= big - 1;
-          const uint32_t blb = __shfl_sync(0xffffffffu, lb[j], src);
-          const uint32_t bub = blb + __shfl_sync(0xffffffffu, len[j], src);
-          const uint32_t n = warp_scan_range<false>(a, blb, bub, __shfl_sync(0xffffffffu, ql[j], src),
-                                                    __shfl_sync(0xffffffffu, qh[j], src), lane, 0, 0);
-          if (lane == src) c = n;
-        }
-        if (q0 + j < a.n_q) a.any[q0 + j] = c ? 1 : 0;
+    for (int j = 0; j < kQPT; ++j) {
+      big[j] = len[j] > kScalarMax;
+      lane_big |= big[j];
+      ub[j] = big[j] ? exact_upper_bound(a, lb[j], len[j], qh[j]) : lb[j] + len[j];
+      cnt[j] = __popc(mask[j]);
+    }
+    const bool warp_big = __any_sync(0xffffffffu, lane_big);
+    if (MODE == kModeAny) {
+      if (warp_big) {
+        const uint4 c4 = long_ranges<false>(long_ctx(a), lane, pack_bits(big), make_uint4(lb[0], lb[1], lb[2], lb[3]),
+                                            make_uint4(ub[0], ub[1], ub[2], ub[3]),
+                                            make_uint4(ql[0], ql[1], ql[2], ql[3]), make_uint4(0, 0, 0, 0), 0,
+                                            0, 0, 0, 0);
+        const uint32_t cl[kQPT] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+        for (int j = 0; j < kQPT; ++j)
+          if (big[j]) cnt[j] = cl[j];
       }
+#pragma unroll
+      for (int j = 0; j < kQPT; ++j)
+        if (q0 + j < a.n_q) a.any[q0 + j] = cnt[j] ? 1 : 0;
       continue;
     }
     uint64_t off[kQPT];
 #pragma unroll
-    for (int j = 0; j < kQPT; ++j) off[j] = (q0 + j < a.n_q) ? a.offsets[q0 + j] : 0ull;
-    emit_short<true>(a, st, warp, lane, mask, lb, off, 0, a.qid_base + w0);
-#pragma unroll
     for (int j = 0; j < kQPT; ++j) {
-      unsigned big = __ballot_sync(0xffffffffu, len[j] > kScalarMax);
-      while (big) {
-        const int src = __ffs(big) - 1;
-        big &= big - 1;
-        const uint32_t blb = __shfl_sync(0xffffffffu, lb[j], src);
-        const uint32_t bub = blb + __shfl_sync(0xffffffffu, len[j], src);
-        warp_scan_range<true>(a, blb, bub, __shfl_sync(0xffffffffu, ql[j], src),
-                              __shfl_sync(0xffffffffu, qh[j], src), lane, shfl_u64(off[j], src),
-                              a.qid_base + w0 + (uint32_t)src * kQPT + j);
-      }
+      off[j] = (q0 + j < a.n_q) ? a.offsets[q0 + j] : 0ull;
+      // hits of a long range = next offset - this offset (the caller's offsets come from the count call)
+      if (big[j]) cnt[j] = (uint32_t)(a.offsets[q0 + j + 1] - off[j]);
     }
+    emit_short<true>(a, st, warp, lane, mask, lb, off, 0, a.qid_base + w0);
+    if (warp_big)
+      long_ranges<true>(long_ctx(a), lane, pack_bits(big), make_uint4(lb[0], lb[1], lb[2], lb[3]),
+                        make_uint4(ub[0], ub[1], ub[2], ub[3]), make_uint4(ql[0], ql[1], ql[2], ql[3]),
+                        make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]), off[0], off[1], off[2], off[3],
+                        a.qid_base + w0);
   }
 }
 
@@ -593,6 +753,7 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
   }
   JoinArgs a;
   a.lowhigh = ix->d_lowhigh;
+  a.high = ix->d_high;
   a.ids = ix->d_id;
   a.dir = ix->d_dir;
   a.groups = ix->d_groups;
@@ -615,6 +776,7 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
   a.qid_base = query_id_base;
   a.st_lb = nullptr;
   a.st_w = nullptr;
+  a.st_ub = nullptr;
   a.cta_total = nullptr;
   a.base_in = d_offset_base;
   const uint64_t n_tiles = (n_q + kCtaTile - 1) / kCtaTile;
@@ -633,10 +795,11 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
   const uint64_t padded = n_tiles * kCtaTile;
   void* scratch = nullptr;
   const uint64_t grid_even = ((uint64_t)grid + 1) & ~1ull;  // keeps the state arrays 16-byte aligned
-  BCU_CUDA(cudaMallocAsync(&scratch, padded * 8 + grid_even * 8, stream));
+  BCU_CUDA(cudaMallocAsync(&scratch, padded * 12 + grid_even * 8, stream));
   a.cta_total = reinterpret_cast<uint64_t*>(scratch);
   a.st_lb = reinterpret_cast<uint32_t*>(a.cta_total + grid_even);
   a.st_w = a.st_lb + padded;
+  a.st_ub = a.st_w + padded;
   probe_kernel<<<grid, kJoinThreads, 0, stream>>>(a);
   BCU_LAUNCHED();
   if (mode == kModeFused) emit_kernel<true><<<grid, kJoinThreads, 0, stream>>>(a);
