@@ -70,3 +70,68 @@ def canonical(offsets, targets):
     from oracle import sort_within_segments
     return np.asarray(offsets, np.uint64), sort_within_segments(np.asarray(offsets, np.uint64),
                                                                 np.asarray(targets, np.uint32))
+
+
+# ---- synthetic sv2nl inputs (text VCFs with every record type the three mappers read) -----------------
+SYNTH_CONTIGS = [("chr1", 2_000_000), ("chr2", 1_500_000), ("chr10", 1_200_000), ("chrX", 900_000),
+                 ("chrUn_KI270302v1", 2274), ("chr1_KI270706v1_random", 175055)]
+
+
+def write_synth_vcfs(directory, seed=1, n_sv=3000, n_nl=2000):
+    """Delly-style SV VCF (DUP/INV/BND/DEL) + ScanNLS-style NL VCF (TDUP/INV/TRA/INS). NL records are
+    jittered copies of SV records (so the filters see near hits, containments, strand cases, duplicates,
+    POS > END swaps, records on '_' contigs) plus random noise. Returns (nl_path, sv_path)."""
+    import os
+    rng = np.random.default_rng(seed)
+    names = [c for c, _ in SYNTH_CONTIGS]
+    lens = dict(SYNTH_CONTIGS)
+    head = ["##fileformat=VCFv4.2"] + [f"##contig=<ID={c},length={l}>" for c, l in SYNTH_CONTIGS]
+    head.append("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO")
+    sv_lines, nl_lines, sv_recs = [], [], []
+    for i in range(n_sv):
+        t = rng.choice(["DUP", "INV", "BND", "DEL"], p=[0.4, 0.25, 0.3, 0.05])
+        c = names[rng.integers(0, 5)]
+        L = int(rng.integers(1, 40_000))
+        p = int(rng.integers(1, max(2, lens[c] - L)))
+        if t == "BND":
+            c2 = names[rng.integers(0, 4)]
+            p2 = int(rng.integers(1, lens[c2]))
+            sv_lines.append(f"{c}\t{p}\tsv{i}\tN\t<BND>\t.\tPASS\tSVTYPE=BND;CHR2={c2};POS2={p2}")
+            sv_recs.append((t, c, p, c2, p2))
+        else:
+            e = p + L
+            if rng.random() < 0.1:
+                p, e = e, p  # POS > END: validate_record swaps
+            sv_lines.append(f"{c}\t{p}\tsv{i}\tN\t<{t}>\t.\tPASS\tSVTYPE={t};END={e}")
+            sv_recs.append((t, c, p, c, e))
+    for i in range(n_nl):
+        if rng.random() < 0.75:
+            t, c, p, c2, e = sv_recs[rng.integers(0, n_sv)]
+            j = lambda: int(rng.integers(-3000, 3000))
+            p, e = max(1, p + j()), max(1, e + j())
+            kind = {"DUP": "TDUP", "INV": "INV", "BND": "TRA", "DEL": "INS"}[t]
+            if rng.random() < 0.15:
+                p, e = e, p
+                if kind == "TRA":
+                    c, c2 = c2, c
+        else:
+            kind = rng.choice(["TDUP", "INV", "TRA", "INS"])
+            c = names[rng.integers(0, 6)]
+            c2 = names[rng.integers(0, 4)] if kind == "TRA" else c
+            p = int(rng.integers(1, lens[c]))
+            e = int(rng.integers(1, lens[c2]))
+        s1, s2 = rng.choice(["+", "-"]), rng.choice(["+", "-"])
+        info = f"SVTYPE={kind};CHR2={c2};SVEND={e}"
+        if rng.random() < 0.9:
+            info += f";STRAND1={s1}" + (f";STRAND2={s2}" if rng.random() < 0.95 else "")
+        line = f"{c}\t{p}\tnl{i}\tN\t<{kind}>\t.\t.\t{info}"
+        nl_lines.append(line)
+        if rng.random() < 0.05:
+            nl_lines.append(line)  # exact duplicate: SV2NL_USE_CACHE writes it once
+    nl_path, sv_path = os.path.join(directory, "nl.vcf"), os.path.join(directory, "sv.vcf.gz")
+    with open(nl_path, "w") as fh:
+        fh.write("\n".join(head + nl_lines) + "\n")
+    import gzip
+    with gzip.open(sv_path, "wt") as fh:
+        fh.write("\n".join(head + sv_lines) + "\n")
+    return nl_path, sv_path
