@@ -63,6 +63,16 @@ struct GroupDesc {
 
 constexpr int kMaxSmemGroups = 256;
 
+// One directory entry = 16 bytes, read with a single 128-bit load: the two bounds of bin b plus the
+// first candidate row, so a sparse query whose candidate range has one row needs ONE dependent access.
+struct __align__(16) DirEntry {
+  uint32_t lb;    // first row of the group with runmax >= b*W
+  uint32_t ub;    // first row of the group with low >= (b+1)*W
+  uint32_t low0;  // {low, high} of row lb (unspecified past the group's end; guarded by ub - lb)
+  uint32_t high0;
+};
+constexpr uint32_t kInlineRows = 1;
+
 }  // namespace bcu
 
 struct bcu_index {
@@ -79,7 +89,7 @@ struct bcu_index {
   uint32_t* d_id = nullptr;          // [n+4] insertion ordinal of each sorted row
   uint32_t* d_runmax = nullptr;      // [n]   running max of high inside the group (max-end array)
   bcu::GroupDesc* d_groups = nullptr;  // [n_groups]
-  uint2* d_dir = nullptr;            // [n_bins] entry b = {first row with runmax >= b*W, first row with low >= (b+1)*W}
+  bcu::DirEntry* d_dir = nullptr;    // [n_bins] see DirEntry
 };
 
 namespace bcu {

@@ -6,11 +6,12 @@
 //   rows sorted by (group, low, id)            <- K1 (radix_sort.cu), stable so ties keep id order
 //   lowhigh[r] = {low, high}, id[r]            <- gather
 //   runmax[r]  = max(high[group_begin..r])     <- segmented running max (scan.cu), the "max-end" array
-//   dir[g][b]  = { first row with runmax >= b*W , first row with low >= (b+1)*W },  W = 1 << shift
+//   dir[g][b]  = { first row with runmax >= b*W , first row with low >= (b+1)*W , {low, high} of that
+//                first row },  W = 1 << shift: 16 bytes, ONE 128-bit load
 // The directory turns both searches of a query (upper bound of q.high in `low`, lower bound of q.low in
-// `runmax`) into ONE 8-byte load when the query lies inside one bin (two otherwise); the few rows of
-// slack it admits are rejected by the exact predicate in the scan (join.cu), so results do not depend
-// on W.
+// `runmax`) into one load when the query lies inside one bin (two otherwise) and brings the first
+// candidate row along; the few rows of slack it admits are rejected by the exact predicate in the scan
+// (join.cu), so results do not depend on W.
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
@@ -79,7 +80,7 @@ __global__ void group_probe_kernel(const uint32_t* __restrict__ head_rows, uint3
 __global__ void __launch_bounds__(kThreads)
     fill_directory_kernel(const GroupDesc* __restrict__ groups, uint32_t n_groups, uint32_t shift,
                           const uint2* __restrict__ lowhigh, const uint32_t* __restrict__ runmax,
-                          uint2* __restrict__ dir, uint64_t n_bins) {
+                          DirEntry* __restrict__ dir, uint64_t n_bins) {
   uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_bins) return;
   // group owning entry e: last descriptor with bin_base <= e
@@ -106,7 +107,13 @@ __global__ void __launch_bounds__(kThreads)
     }
     ub = a;
   }
-  dir[e] = make_uint2(lb, ub);
+  DirEntry de;
+  de.lb = lb;
+  de.ub = ub;
+  const uint2 r0 = (lb < g.row_end) ? lowhigh[lb] : make_uint2(0xffffffffu, 0u);
+  de.low0 = r0.x;
+  de.high0 = r0.y;
+  dir[e] = de;
 }
 
 static double env_double(const char* name, double dflt) {
@@ -220,7 +227,7 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
   BCU_CUDA(cudaStreamSynchronize(stream));
 
   // ---- bin width: smallest shift whose directory stays within ~bin_factor entries per target ----
-  const double factor = env_double("BCU_BIN_FACTOR", 4.0);
+  const double factor = env_double("BCU_BIN_FACTOR", 2.0);
   const uint64_t budget = std::max<uint64_t>((uint64_t)(factor * (double)n), 1024) + 2ull * n_groups;
   uint32_t shift = 0;
   uint64_t n_bins = 0;
@@ -245,8 +252,8 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
   ix->shift = shift;
   ix->n_bins = n_bins;
   BCU_CUDA(cudaMalloc((void**)&ix->d_groups, (size_t)n_groups * sizeof(GroupDesc)));
-  BCU_CUDA(cudaMalloc((void**)&ix->d_dir, n_bins * sizeof(uint2)));
-  ix->bytes += (uint64_t)n_groups * sizeof(GroupDesc) + n_bins * sizeof(uint2);
+  BCU_CUDA(cudaMalloc((void**)&ix->d_dir, n_bins * sizeof(DirEntry)));
+  ix->bytes += (uint64_t)n_groups * sizeof(GroupDesc) + n_bins * sizeof(DirEntry);
   BCU_CUDA(cudaMemcpyAsync(ix->d_groups, descs.data(), (size_t)n_groups * sizeof(GroupDesc),
                            cudaMemcpyHostToDevice, stream));
   fill_directory_kernel<<<(unsigned)((n_bins + kThreads - 1) / kThreads), kThreads, 0, stream>>>(

@@ -12,9 +12,9 @@
 //   probe_kernel   K3. The query batch is cut into contiguous chunks, one per CTA; inside a chunk every
 //                  WARP takes 128 consecutive queries at a time (4 per lane, one 128-bit load per input
 //                  column) and never synchronises with other warps.
-//                    bounds: lb = dir[bin(q.low)].lb, ub = dir[bin(q.high)].ub -- ONE 8-byte load when the
-//                            query lies inside one directory bin (the directory replaces both binary
-//                            searches; index_build.cu)
+//                    bounds: lb = dir[bin(q.low)].lb, ub = dir[bin(q.high)].ub -- ONE 128-bit load when the
+//                            query lies inside one directory bin, which also brings the first candidate
+//                            row (the directory replaces both binary searches; index_build.cu)
 //                    count : rows [lb,ub) are a superset of the hits; the exact predicate
 //                            q.low <= t.high && t.low <= q.high (interval_tree.hpp:119-121) is evaluated
 //                            on each. Short ranges: by the owning lane, its 4 queries interleaved so
@@ -58,7 +58,7 @@ struct JoinArgs {
   const uint2* __restrict__ lowhigh;
   const uint32_t* __restrict__ high;  // SoA copy of lowhigh[].y, padded: the long-range path streams it
   const uint32_t* __restrict__ ids;
-  const uint2* __restrict__ dir;
+  const DirEntry* __restrict__ dir;
   const GroupDesc* __restrict__ groups;
   uint32_t n_groups;
   uint32_t shift;
@@ -164,11 +164,12 @@ __device__ __forceinline__ void load_queries(const JoinArgs& a, uint32_t q0, uin
 // K3 step 1: candidate row range [lb, lb+len) of one query. `valid` = the query exists.
 __device__ __forceinline__ void query_bounds(const JoinArgs& a, const GroupTables& tb, bool valid,
                                              uint32_t ql, uint32_t qh, uint32_t qg, uint32_t& lb,
-                                             uint32_t& len) {
+                                             uint32_t& len, uint32_t& inline_mask) {
   const bool in_smem = a.n_groups <= (uint32_t)kMaxSmemGroups;
   const bool direct = in_smem && a.max_gval < (uint32_t)kDirectGroups;
   lb = 0;
   len = 0;
+  inline_mask = 0;
   uint32_t nb = 0;
   uint64_t bin_base = 0;
   if (valid) {
@@ -195,11 +196,13 @@ __device__ __forceinline__ void query_bounds(const JoinArgs& a, const GroupTable
   if (b_lo < nb) {  // otherwise unknown group, or q.low lies beyond every high of the group
     uint32_t b_hi = qh >> a.shift;
     if (b_hi >= nb) b_hi = nb - 1u;
-    const uint2 e = ldg_u2(a.dir + bin_base + b_lo);  // {lb(b_lo), ub(b_lo + 1)}: all a one-bin query needs
+    // {lb(b_lo), ub(b_lo + 1), row lb}: all a one-bin query with one candidate needs
+    const uint4 e = ldg_u4(reinterpret_cast<const uint4*>(a.dir + bin_base + b_lo));
     uint32_t u = e.y;
-    if (b_hi != b_lo) u = ldg_u2(a.dir + bin_base + b_hi).y;
+    if (b_hi != b_lo) u = a.dir[bin_base + b_hi].ub;
     lb = e.x;
     len = u > e.x ? u - e.x : 0u;
+    inline_mask = (uint32_t)(len > 0 && overlaps(ql, qh, e.z, e.w));
   }
 }
 
@@ -207,13 +210,14 @@ __device__ __forceinline__ void query_bounds(const JoinArgs& a, const GroupTable
 __device__ __forceinline__ void scan_short(const JoinArgs& a, const uint32_t (&ql)[kQPT],
                                            const uint32_t (&qh)[kQPT], const uint32_t (&lb)[kQPT],
                                            const uint32_t (&len)[kQPT], uint32_t (&mask)[kQPT]) {
+  // on entry mask[j] holds the bit of the row that came inline with the directory entry
   uint32_t max_short = 0;
 #pragma unroll
   for (int j = 0; j < kQPT; ++j) {
-    mask[j] = 0;
-    if (len[j] <= kScalarMax && len[j] > max_short) max_short = len[j];
+    if (len[j] > kScalarMax) mask[j] = 0;
+    else if (len[j] > max_short) max_short = len[j];
   }
-  for (uint32_t k = 0; k < max_short; ++k) {
+  for (uint32_t k = kInlineRows; k < max_short; ++k) {
 #pragma unroll
     for (int j = 0; j < kQPT; ++j) {
       if (k < len[j] && len[j] <= kScalarMax) {
@@ -487,7 +491,7 @@ __global__ void __launch_bounds__(kJoinThreads, kProbeMinBlocks) probe_kernel(co
 
     uint32_t lb[kQPT], len[kQPT], w[kQPT];
 #pragma unroll
-    for (int j = 0; j < kQPT; ++j) query_bounds(a, tb, q0 + j < a.n_q, ql[j], qh[j], qg[j], lb[j], len[j]);
+    for (int j = 0; j < kQPT; ++j) query_bounds(a, tb, q0 + j < a.n_q, ql[j], qh[j], qg[j], lb[j], len[j], w[j]);
     scan_short(a, ql, qh, lb, len, w);
     bool big[kQPT];
     uint32_t ub[kQPT];
@@ -673,7 +677,7 @@ __global__ void __launch_bounds__(kJoinThreads, kJoinMinBlocks) direct_kernel(co
     uint32_t ql[kQPT], qh[kQPT], qg[kQPT], lb[kQPT], len[kQPT], mask[kQPT];
     load_queries(a, q0, ql, qh, qg);
 #pragma unroll
-    for (int j = 0; j < kQPT; ++j) query_bounds(a, tb, q0 + j < a.n_q, ql[j], qh[j], qg[j], lb[j], len[j]);
+    for (int j = 0; j < kQPT; ++j) query_bounds(a, tb, q0 + j < a.n_q, ql[j], qh[j], qg[j], lb[j], len[j], mask[j]);
     scan_short(a, ql, qh, lb, len, mask);
     bool big[kQPT];
     uint32_t ub[kQPT], cnt[kQPT];
