@@ -79,6 +79,8 @@ struct bcu_index {
   int device = 0;
   uint64_t n = 0;
   uint32_t n_groups = 0;
+  uint32_t n_comp = 1;          // length-class slots a query probes: 1, 2 or 4 (join.cu: virtual queries)
+  uint32_t class_base_len = 0;  // class c holds lengths < class_base_len * 4^c
   uint32_t shift = 0;
   uint32_t max_gval = 0;  // largest group value (selects the direct group map in join.cu)
   uint32_t sort_passes = 0;
@@ -88,7 +90,7 @@ struct bcu_index {
   uint32_t* d_high = nullptr;        // [n+4] `high` of the same rows as a plain column (long-range scans)
   uint32_t* d_id = nullptr;          // [n+4] insertion ordinal of each sorted row
   uint32_t* d_runmax = nullptr;      // [n]   running max of high inside the group (max-end array)
-  bcu::GroupDesc* d_groups = nullptr;  // [n_groups]
+  bcu::GroupDesc* d_groups = nullptr;  // [n_comp][n_groups], empty slots have nb == 0
   bcu::DirEntry* d_dir = nullptr;    // [n_bins] see DirEntry
 };
 
@@ -102,7 +104,7 @@ int radix_sort_pairs(uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uint3
 
 // Generic decoupled look-back scans (scan.cu)
 int exclusive_sum_u32(const uint32_t* d_in, uint32_t* d_out, uint64_t n, cudaStream_t stream);
-int segmented_running_max(const uint64_t* d_keys /* group in the high 32 bits */, const uint32_t* d_val,
+int segmented_running_max(const uint64_t* d_segkey /* equal within a segment */, const uint32_t* d_val,
                           uint32_t* d_out, uint64_t n, cudaStream_t stream);
 
 // K3/K4 (join.cu)

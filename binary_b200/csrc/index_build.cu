@@ -3,7 +3,9 @@
 // Reference being replaced: IntervalTree::insert_node_impl + max maintenance
 // (interval_tree.hpp:230-260, 206-228, 262-278): a BST on `low` whose nodes carry the subtree max of
 // `high`. Flat equivalent (NCList/AIList style):
-//   rows sorted by (group, low, id)            <- K1 (radix_sort.cu), stable so ties keep id order
+//   rows sorted by (class, group, low, id)     <- K1 (radix_sort.cu), stable so ties keep id order; `class`
+//                                                 is the length class of the AIList-style decomposition
+//                                                 (one class unless some targets are far longer than others)
 //   lowhigh[r] = {low, high}, id[r]            <- gather
 //   runmax[r]  = max(high[group_begin..r])     <- segmented running max (scan.cu), the "max-end" array
 //   dir[g][b]  = { first row with runmax >= b*W , first row with low >= (b+1)*W , {low, high} of that
@@ -41,37 +43,87 @@ __global__ void __launch_bounds__(kThreads)
   if ((threadIdx.x & 31) == 0 && diff) atomicOr(varying, (unsigned long long)diff);
 }
 
-// sorted rows -> {low, high} + id (+ a plain `high` column for the scan); group heads are appended to
-// head_rows in arbitrary order (the host sorts them: there are few).
+// sorted rows -> {low, high}, id, plain `high` column and the segment key (= group value); segment heads
+// are appended to head_rows in arbitrary order (the host sorts them: there are few).
 __global__ void __launch_bounds__(kThreads)
     gather_rows_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                        const uint32_t* __restrict__ high, uint64_t n, uint2* __restrict__ lowhigh,
                        uint32_t* __restrict__ ids, uint32_t* __restrict__ high_sorted,
-                       uint32_t* __restrict__ head_rows, uint32_t* n_heads) {
+                       uint64_t* __restrict__ segkey, uint32_t* __restrict__ head_rows, uint32_t* n_heads,
+                       uint32_t* max_len, unsigned long long* sum_len) {
   uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n) return;
-  uint64_t k = keys[r];
-  uint32_t id = vals[r];
-  uint32_t h = high[id];
-  lowhigh[r] = make_uint2((uint32_t)k, h);
-  ids[r] = id;
-  high_sorted[r] = h;
-  if (r == 0 || (uint32_t)(keys[r - 1] >> 32) != (uint32_t)(k >> 32)) {
-    uint32_t slot = atomicAdd(n_heads, 1u);
-    head_rows[slot] = (uint32_t)r;
+  uint32_t len = 0;
+  if (r < n) {
+    uint64_t k = keys[r];
+    uint32_t id = vals[r];
+    uint32_t h = high[id];
+    uint32_t l = (uint32_t)k;
+    lowhigh[r] = make_uint2(l, h);
+    ids[r] = id;
+    high_sorted[r] = h;
+    segkey[r] = k >> 32;
+    len = h >= l ? h - l : 0u;  // inverted rows count as length 0
+    if (r == 0 || (keys[r - 1] >> 32) != (k >> 32)) head_rows[atomicAdd(n_heads, 1u)] = (uint32_t)r;
+  }
+  unsigned long long total = len;
+#pragma unroll
+  for (int off = 16; off; off >>= 1) {
+    len = max(len, __shfl_xor_sync(0xffffffffu, len, off));
+    total += __shfl_xor_sync(0xffffffffu, total, off);
+  }
+  if ((threadIdx.x & 31) == 0 && len) {
+    atomicMax(max_len, len);
+    atomicAdd(sum_len, total);
   }
 }
 
-// per group: value, last row's low and runmax (= max high of the group) -> host picks the bin width
-__global__ void group_probe_kernel(const uint32_t* __restrict__ head_rows, uint32_t n_groups, uint64_t n,
-                                   const uint64_t* __restrict__ keys, const uint32_t* __restrict__ runmax,
-                                   uint32_t* __restrict__ gval, uint32_t* __restrict__ cmax) {
+// length class of every row (see build_on_device) as the key of a stable 2-bit partition
+__global__ void __launch_bounds__(kThreads)
+    length_class_kernel(const uint2* __restrict__ lowhigh, uint64_t n, uint32_t base_len, uint32_t n_class,
+                        uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const uint2 t = lowhigh[r];
+  const uint64_t len = t.y >= t.x ? (uint64_t)(t.y - t.x) : 0ull;
+  uint32_t c = 0;
+  uint64_t limit = base_len;  // class c holds lengths < base_len * 4^c (last class: everything else)
+  while (c + 1 < n_class && len >= limit) { ++c; limit *= 4; }
+  keys[r] = c;
+  vals[r] = (uint32_t)r;
+}
+
+// rows permuted into (component, group, low) order
+__global__ void __launch_bounds__(kThreads)
+    permute_rows_kernel(const uint64_t* __restrict__ comp_sorted, const uint32_t* __restrict__ perm, uint64_t n,
+                        const uint2* __restrict__ lowhigh_in, const uint32_t* __restrict__ ids_in,
+                        const uint64_t* __restrict__ segkey_in, uint2* __restrict__ lowhigh,
+                        uint32_t* __restrict__ ids, uint32_t* __restrict__ high, uint64_t* __restrict__ segkey,
+                        uint32_t* __restrict__ head_rows, uint32_t* n_heads) {
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const uint32_t src = perm[r];
+  const uint2 t = lowhigh_in[src];
+  lowhigh[r] = t;
+  ids[r] = ids_in[src];
+  high[r] = t.y;
+  const uint64_t sk = (comp_sorted[r] << 32) | segkey_in[src];  // component in bits 32.., group below
+  segkey[r] = sk;
+  bool head = (r == 0);
+  if (!head) head = ((comp_sorted[r - 1] << 32) | segkey_in[perm[r - 1]]) != sk;
+  if (head) head_rows[atomicAdd(n_heads, 1u)] = (uint32_t)r;
+}
+
+// per segment: key, last row's low and runmax (= max high of the segment) -> host picks the bin width
+__global__ void group_probe_kernel(const uint32_t* __restrict__ head_rows, uint32_t n_segs, uint64_t n,
+                                   const uint64_t* __restrict__ segkey, const uint2* __restrict__ lowhigh,
+                                   const uint32_t* __restrict__ runmax, uint64_t* __restrict__ seg_out,
+                                   uint32_t* __restrict__ cmax) {
   uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n_groups) return;
+  if (g >= n_segs) return;
   uint32_t b = head_rows[g];
-  uint64_t e = (g + 1 < n_groups) ? head_rows[g + 1] : n;
-  gval[g] = (uint32_t)(keys[b] >> 32);
-  uint32_t last_low = (uint32_t)keys[e - 1];
+  uint64_t e = (g + 1 < n_segs) ? head_rows[g + 1] : n;
+  seg_out[g] = segkey[b];
+  uint32_t last_low = lowhigh[e - 1].x;
   uint32_t mh = runmax[e - 1];
   cmax[g] = last_low > mh ? last_low : mh;
 }
@@ -83,7 +135,7 @@ __global__ void __launch_bounds__(kThreads)
                           DirEntry* __restrict__ dir, uint64_t n_bins) {
   uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_bins) return;
-  // group owning entry e: last descriptor with bin_base <= e
+  // segment owning entry e: last descriptor with bin_base <= e
   uint32_t lo = 0, hi = n_groups;
   while (hi - lo > 1) {
     uint32_t mid = (lo + hi) >> 1;
@@ -163,22 +215,62 @@ static void keep_pool_warm(int device) {
   done.fetch_or(1ull << device);
 }
 
+static int alloc_rows(bcu_index* ix, uint64_t n, cudaStream_t stream) {
+  BCU_CUDA(cudaMalloc((void**)&ix->d_lowhigh, (n + 2) * sizeof(uint2)));  // +pad: join.cu reads row pairs
+  BCU_CUDA(cudaMalloc((void**)&ix->d_id, (n + 4) * 4));                   // +pad: 128-bit loads of 4 rows
+  BCU_CUDA(cudaMalloc((void**)&ix->d_high, (n + 4) * 4));
+  BCU_CUDA(cudaMemsetAsync(ix->d_lowhigh + n, 0, 2 * sizeof(uint2), stream));
+  BCU_CUDA(cudaMemsetAsync(ix->d_id + n, 0, 16, stream));
+  BCU_CUDA(cudaMemsetAsync(ix->d_high + n, 0, 16, stream));
+  return BCU_OK;
+}
+
+// heads (unordered, on device) -> sorted on the host -> segment keys and max coordinates
+static int probe_segments(const bcu_index* ix, uint64_t n, uint32_t* head_rows, uint32_t* d_n_heads,
+                          const uint64_t* segkey, TempBuffers& tmp, cudaStream_t stream,
+                          std::vector<uint32_t>& heads, std::vector<uint64_t>& seg, std::vector<uint32_t>& cmax) {
+  uint32_t n_segs = 0;
+  BCU_CUDA(cudaMemcpyAsync(&n_segs, d_n_heads, 4, cudaMemcpyDeviceToHost, stream));
+  BCU_CUDA(cudaStreamSynchronize(stream));
+  heads.resize(n_segs);
+  BCU_CUDA(cudaMemcpyAsync(heads.data(), head_rows, (size_t)n_segs * 4, cudaMemcpyDeviceToHost, stream));
+  BCU_CUDA(cudaStreamSynchronize(stream));
+  std::sort(heads.begin(), heads.end());
+  BCU_CUDA(cudaMemcpyAsync(head_rows, heads.data(), (size_t)n_segs * 4, cudaMemcpyHostToDevice, stream));
+  uint64_t* d_seg;
+  uint32_t* d_cmax;
+  BCU_CUDA(tmp.alloc(&d_seg, n_segs));
+  BCU_CUDA(tmp.alloc(&d_cmax, n_segs));
+  group_probe_kernel<<<(n_segs + kThreads - 1) / kThreads, kThreads, 0, stream>>>(
+      head_rows, n_segs, n, segkey, ix->d_lowhigh, ix->d_runmax, d_seg, d_cmax);
+  BCU_LAUNCHED();
+  seg.resize(n_segs);
+  cmax.resize(n_segs);
+  BCU_CUDA(cudaMemcpyAsync(seg.data(), d_seg, (size_t)n_segs * 8, cudaMemcpyDeviceToHost, stream));
+  BCU_CUDA(cudaMemcpyAsync(cmax.data(), d_cmax, (size_t)n_segs * 4, cudaMemcpyDeviceToHost, stream));
+  BCU_CUDA(cudaStreamSynchronize(stream));
+  return BCU_OK;
+}
+
 static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, const uint32_t* d_low,
                            const uint32_t* d_high, cudaStream_t stream) {
   ix->n = n;
   keep_pool_warm(ix->device);
   if (n == 0) return BCU_OK;
   TempBuffers tmp(stream);
-  uint64_t *keys_a, *keys_b;
+  uint64_t *keys_a, *keys_b, *segkey;
   uint32_t *vals_a, *vals_b, *head_rows, *counters;
   BCU_CUDA(tmp.alloc(&keys_a, n));
   BCU_CUDA(tmp.alloc(&keys_b, n));
+  BCU_CUDA(tmp.alloc(&segkey, n));
   BCU_CUDA(tmp.alloc(&vals_a, n));
   BCU_CUDA(tmp.alloc(&vals_b, n));
   BCU_CUDA(tmp.alloc(&head_rows, n));
-  BCU_CUDA(tmp.alloc(&counters, 4));  // [0..1] varying bits (u64), [2] n_heads
-  BCU_CUDA(cudaMemsetAsync(counters, 0, 16, stream));
+  BCU_CUDA(tmp.alloc(&counters, 8));  // [0..1] varying bits (u64), [2] n_heads, [3] max length, [4] n_heads #2,
+                                      // [6..7] sum of lengths (u64)
+  BCU_CUDA(cudaMemsetAsync(counters, 0, 32, stream));
 
+  // ---- K1: sort by (group, low) --------------------------------------------------------------------
   const unsigned grid_n = (unsigned)std::min<uint64_t>((n + kThreads - 1) / kThreads, 148ull * 16);
   make_keys_kernel<<<grid_n, kThreads, 0, stream>>>(d_group, d_low, n, keys_a, vals_a,
                                                    reinterpret_cast<unsigned long long*>(counters));
@@ -186,80 +278,131 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
   uint64_t varying = 0;
   BCU_CUDA(cudaMemcpyAsync(&varying, counters, 8, cudaMemcpyDeviceToHost, stream));
   BCU_CUDA(cudaStreamSynchronize(stream));
-
   uint64_t* keys;
   uint32_t* vals;
   BCU_TRY(radix_sort_pairs(keys_a, keys_b, vals_a, vals_b, n, varying, stream, &keys, &vals,
                            &ix->sort_passes));
 
-  BCU_CUDA(cudaMalloc((void**)&ix->d_lowhigh, (n + 2) * sizeof(uint2)));  // +pad: join.cu reads row pairs
-  BCU_CUDA(cudaMemsetAsync(ix->d_lowhigh + n, 0, 2 * sizeof(uint2), stream));
-  BCU_CUDA(cudaMalloc((void**)&ix->d_id, (n + 4) * 4));  // +pad: 128-bit loads of 4 rows
-  BCU_CUDA(cudaMalloc((void**)&ix->d_high, (n + 4) * 4));
-  BCU_CUDA(cudaMemsetAsync(ix->d_id + n, 0, 16, stream));
-  BCU_CUDA(cudaMemsetAsync(ix->d_high + n, 0, 16, stream));
+  // ---- K2: rows, running max, segments ---------------------------------------------------------------
+  BCU_TRY(alloc_rows(ix, n, stream));
   BCU_CUDA(cudaMalloc((void**)&ix->d_runmax, n * 4));
   ix->bytes += n * 20;
   const unsigned grid_rows = (unsigned)((n + kThreads - 1) / kThreads);
   gather_rows_kernel<<<grid_rows, kThreads, 0, stream>>>(keys, vals, d_high, n, ix->d_lowhigh, ix->d_id,
-                                                        ix->d_high, head_rows, counters + 2);
+                                                        ix->d_high, segkey, head_rows, counters + 2,
+                                                        counters + 3,
+                                                        reinterpret_cast<unsigned long long*>(counters + 6));
   BCU_LAUNCHED();
-  BCU_TRY(segmented_running_max(keys, ix->d_high, ix->d_runmax, n, stream));
+  BCU_TRY(segmented_running_max(segkey, ix->d_high, ix->d_runmax, n, stream));
+  std::vector<uint32_t> heads, cmax;
+  std::vector<uint64_t> seg;
+  BCU_TRY(probe_segments(ix, n, head_rows, counters + 2, segkey, tmp, stream, heads, seg, cmax));
+  const uint32_t n_groups = (uint32_t)heads.size();
+  std::vector<uint32_t> gval(n_groups);
+  uint64_t span = 0;
+  for (uint32_t g = 0; g < n_groups; ++g) { gval[g] = (uint32_t)seg[g]; span += (uint64_t)cmax[g] + 1; }
 
-  // ---- groups: sort the head rows on the host (few), probe value / max coordinate per group ----
-  uint32_t n_groups = 0;
-  BCU_CUDA(cudaMemcpyAsync(&n_groups, counters + 2, 4, cudaMemcpyDeviceToHost, stream));
+  // ---- length classes (AIList-style decomposition) -------------------------------------------------
+  // A target much longer than its neighbours drags the running max along and with it the first candidate
+  // row of every later query. Targets are therefore split by length into up to 4 classes, each a 4x band
+  // above base_len = max(16 * mean spacing of starts, 2 * mean length): inside a class the candidate window
+  // of a query is at most ~4x the rows it can hit, and a handful of giant intervals ends up in a class of
+  // its own. A broad but outlier-free length distribution (max < 4x that base) stays ONE class: splitting
+  // it would only fragment the long-range scans. Classes become the top sort key (class, group, low); a
+  // query probes every class slot.
+  uint32_t max_len = 0;
+  uint64_t sum_len = 0;
+  BCU_CUDA(cudaMemcpyAsync(&max_len, counters + 3, 4, cudaMemcpyDeviceToHost, stream));
+  BCU_CUDA(cudaMemcpyAsync(&sum_len, counters + 6, 8, cudaMemcpyDeviceToHost, stream));
   BCU_CUDA(cudaStreamSynchronize(stream));
-  std::vector<uint32_t> heads(n_groups);
-  BCU_CUDA(cudaMemcpyAsync(heads.data(), head_rows, (size_t)n_groups * 4, cudaMemcpyDeviceToHost, stream));
-  BCU_CUDA(cudaStreamSynchronize(stream));
-  std::sort(heads.begin(), heads.end());
-  BCU_CUDA(cudaMemcpyAsync(head_rows, heads.data(), (size_t)n_groups * 4, cudaMemcpyHostToDevice, stream));
-  uint32_t *d_gval, *d_cmax;
-  BCU_CUDA(tmp.alloc(&d_gval, n_groups));
-  BCU_CUDA(tmp.alloc(&d_cmax, n_groups));
-  group_probe_kernel<<<(n_groups + kThreads - 1) / kThreads, kThreads, 0, stream>>>(
-      head_rows, n_groups, n, keys, ix->d_runmax, d_gval, d_cmax);
-  BCU_LAUNCHED();
-  std::vector<uint32_t> gval(n_groups), cmax(n_groups);
-  BCU_CUDA(cudaMemcpyAsync(gval.data(), d_gval, (size_t)n_groups * 4, cudaMemcpyDeviceToHost, stream));
-  BCU_CUDA(cudaMemcpyAsync(cmax.data(), d_cmax, (size_t)n_groups * 4, cudaMemcpyDeviceToHost, stream));
-  BCU_CUDA(cudaStreamSynchronize(stream));
+  const double spacing = (double)span / (double)n, mean_len = (double)sum_len / (double)n;
+  const double base_d = std::min(4.0e9, std::max({1.0, env_double("BCU_CLASS_SPACINGS", 16.0) * spacing,
+                                                  env_double("BCU_CLASS_MEANS", 2.0) * mean_len}));
+  const uint32_t base_len = (uint32_t)base_d;
+  uint32_t n_class = 1;
+  for (uint64_t limit = base_len; n_class < 4 && (uint64_t)max_len >= limit; limit *= 4) ++n_class;
+  if (env_double("BCU_MAX_CLASSES", 4.0) < n_class) n_class = (uint32_t)env_double("BCU_MAX_CLASSES", 4.0);
+  const uint32_t n_comp = n_class <= 1 ? 1u : (n_class == 2 ? 2u : 4u);  // slots: 1, 2 or 4 (see join.cu)
+
+  if (n_comp > 1) {
+    // stable partition of the sorted rows by class (one 2-bit radix pass), then permute
+    length_class_kernel<<<grid_rows, kThreads, 0, stream>>>(ix->d_lowhigh, n, base_len, n_class, keys_a, vals_a);
+    BCU_LAUNCHED();
+    uint64_t* comp_sorted;
+    uint32_t* perm;
+    uint32_t passes = 0;
+    BCU_TRY(radix_sort_pairs(keys_a, keys_b, vals_a, vals_b, n, 3ull, stream, &comp_sorted, &perm, &passes));
+    ix->sort_passes += passes;
+    uint64_t* segkey2;
+    BCU_CUDA(tmp.alloc(&segkey2, n));
+    bcu_index old = *ix;  // the (group, low)-ordered arrays become the source of the permutation
+    ix->d_lowhigh = nullptr; ix->d_id = nullptr; ix->d_high = nullptr;
+    int rc = alloc_rows(ix, n, stream);
+    if (rc == BCU_OK) {
+      permute_rows_kernel<<<grid_rows, kThreads, 0, stream>>>(comp_sorted, perm, n, old.d_lowhigh, old.d_id, segkey,
+                                                            ix->d_lowhigh, ix->d_id, ix->d_high, segkey2,
+                                                            head_rows, counters + 4);
+      if (cudaGetLastError() != cudaSuccess) rc = BCU_E_CUDA;
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    if (rc == BCU_OK && cudaStreamSynchronize(stream) != cudaSuccess) rc = BCU_E_CUDA;
+    cudaFree(old.d_lowhigh); cudaFree(old.d_id); cudaFree(old.d_high);
+    if (rc != BCU_OK) { set_error("index build: permuting rows into length classes failed"); return rc; }
+    segkey = segkey2;
+    BCU_TRY(segmented_running_max(segkey, ix->d_high, ix->d_runmax, n, stream));
+    BCU_TRY(probe_segments(ix, n, head_rows, counters + 4, segkey, tmp, stream, heads, seg, cmax));
+  }
+  const uint32_t n_segs = (uint32_t)heads.size();
 
   // ---- bin width: smallest shift whose directory stays within ~bin_factor entries per target ----
   const double factor = env_double("BCU_BIN_FACTOR", 2.0);
-  const uint64_t budget = std::max<uint64_t>((uint64_t)(factor * (double)n), 1024) + 2ull * n_groups;
+  const uint64_t budget = std::max<uint64_t>((uint64_t)(factor * (double)n), 1024) + 2ull * n_segs;
   uint32_t shift = 0;
   uint64_t n_bins = 0;
   for (shift = 0; shift <= 31; ++shift) {
     n_bins = 0;
-    for (uint32_t g = 0; g < n_groups; ++g) n_bins += ((uint64_t)cmax[g] >> shift) + 1;
+    for (uint32_t g = 0; g < n_segs; ++g) n_bins += ((uint64_t)cmax[g] >> shift) + 1;
     if (n_bins <= budget) break;
   }
   if (shift > 31) shift = 31;
-  std::vector<GroupDesc> descs(n_groups);
+  // compact list of the segments that exist (directory fill) + the query-side table [component][group]
+  std::vector<GroupDesc> segs(n_segs), table((size_t)n_comp * n_groups);
+  for (uint32_t c = 0; c < n_comp; ++c)
+    for (uint32_t g = 0; g < n_groups; ++g) {
+      GroupDesc& d = table[(size_t)c * n_groups + g];
+      d.gval = gval[g]; d.row_begin = d.row_end = 0; d.nb = 0; d.bin_base = 0;
+    }
   n_bins = 0;
-  for (uint32_t g = 0; g < n_groups; ++g) {
-    descs[g].gval = gval[g];
-    descs[g].row_begin = heads[g];
-    descs[g].row_end = (g + 1 < n_groups) ? heads[g + 1] : (uint32_t)n;
-    descs[g].nb = (uint32_t)(((uint64_t)cmax[g] >> shift) + 1);
-    descs[g].bin_base = n_bins;
-    n_bins += (uint64_t)descs[g].nb;
+  for (uint32_t s = 0; s < n_segs; ++s) {
+    GroupDesc& d = segs[s];
+    d.gval = (uint32_t)seg[s];
+    d.row_begin = heads[s];
+    d.row_end = (s + 1 < n_segs) ? heads[s + 1] : (uint32_t)n;
+    d.nb = (uint32_t)(((uint64_t)cmax[s] >> shift) + 1);
+    d.bin_base = n_bins;
+    n_bins += (uint64_t)d.nb;
+    const uint32_t comp = (uint32_t)(seg[s] >> 32);
+    const uint32_t g = (uint32_t)(std::lower_bound(gval.begin(), gval.end(), d.gval) - gval.begin());
+    table[(size_t)comp * n_groups + g] = d;
   }
   ix->n_groups = n_groups;
+  ix->n_comp = n_comp;
+  ix->class_base_len = base_len;
   ix->max_gval = n_groups ? gval[n_groups - 1] : 0;
   ix->shift = shift;
   ix->n_bins = n_bins;
-  BCU_CUDA(cudaMalloc((void**)&ix->d_groups, (size_t)n_groups * sizeof(GroupDesc)));
+  GroupDesc* d_segs;
+  BCU_CUDA(tmp.alloc(&d_segs, n_segs));
+  BCU_CUDA(cudaMalloc((void**)&ix->d_groups, table.size() * sizeof(GroupDesc)));
   BCU_CUDA(cudaMalloc((void**)&ix->d_dir, n_bins * sizeof(DirEntry)));
-  ix->bytes += (uint64_t)n_groups * sizeof(GroupDesc) + n_bins * sizeof(DirEntry);
-  BCU_CUDA(cudaMemcpyAsync(ix->d_groups, descs.data(), (size_t)n_groups * sizeof(GroupDesc),
+  ix->bytes += table.size() * sizeof(GroupDesc) + n_bins * sizeof(DirEntry);
+  BCU_CUDA(cudaMemcpyAsync(d_segs, segs.data(), (size_t)n_segs * sizeof(GroupDesc), cudaMemcpyHostToDevice, stream));
+  BCU_CUDA(cudaMemcpyAsync(ix->d_groups, table.data(), table.size() * sizeof(GroupDesc),
                            cudaMemcpyHostToDevice, stream));
   fill_directory_kernel<<<(unsigned)((n_bins + kThreads - 1) / kThreads), kThreads, 0, stream>>>(
-      ix->d_groups, n_groups, shift, ix->d_lowhigh, ix->d_runmax, ix->d_dir, n_bins);
+      d_segs, n_segs, shift, ix->d_lowhigh, ix->d_runmax, ix->d_dir, n_bins);
   BCU_LAUNCHED();
-  BCU_CUDA(cudaStreamSynchronize(stream));  // descs/heads are host temporaries
+  BCU_CUDA(cudaStreamSynchronize(stream));  // host vectors are temporaries
   return BCU_OK;
 }
 
@@ -334,7 +477,7 @@ extern "C" int bcu_index_get_info(const bcu_index* ix, bcu_index_info* info) {
   if (!ix || !info) { set_error("bcu_index_get_info: NULL argument"); return BCU_E_INVALID; }
   info->n_targets = ix->n;
   info->n_groups = ix->n_groups;
-  info->n_components = 1;
+  info->n_components = ix->n_comp;
   info->bin_shift = ix->shift;
   info->sort_passes = ix->sort_passes;
   info->n_bins = ix->n_bins;

@@ -66,7 +66,10 @@ struct JoinArgs {
   const uint32_t* __restrict__ qgroup;
   const uint32_t* __restrict__ qlow;
   const uint32_t* __restrict__ qhigh;
-  uint32_t n_q;
+  uint32_t n_q;    // real queries
+  uint32_t n_comp; // length-class slots per query (1, 2 or 4): virtual query v = q * n_comp + slot
+  uint32_t n_vq;   // n_q * n_comp virtual queries: what the kernels iterate over
+  uint32_t comp_shift;  // log2(n_comp)
   uint32_t chunk;  // queries per CTA chunk (multiple of kCtaTile); direct_kernel: unused
   int vec_ok;      // all query columns (and offsets) are 16-byte aligned
   uint64_t* offsets;
@@ -120,32 +123,36 @@ __device__ __forceinline__ bool overlaps(uint32_t ql, uint32_t qh, uint32_t tl, 
 // group tables -> shared memory, once per CTA (ends with a barrier)
 __device__ __forceinline__ void load_group_tables(const JoinArgs& a, GroupTables& tb) {
   const int tid = threadIdx.x;
-  const bool in_smem = a.n_groups <= (uint32_t)kMaxSmemGroups;
+  const uint32_t n_desc = a.n_groups * a.n_comp;  // table layout: [slot][group]
+  const bool in_smem = n_desc <= (uint32_t)kMaxSmemGroups;
   const bool direct = in_smem && a.max_gval < (uint32_t)kDirectGroups;
   if (in_smem) {
     if (direct)
       for (int g = tid; g < kDirectGroups; g += kJoinThreads) tb.g_map[g] = 0xffffu;
     __syncthreads();
-    for (uint32_t g = tid; g < a.n_groups; g += kJoinThreads) {
+    for (uint32_t g = tid; g < n_desc; g += kJoinThreads) {
       const GroupDesc d = a.groups[g];
       tb.g_val[g] = d.gval;
       tb.g_nb[g] = d.nb;
       tb.g_base[g] = d.bin_base;
-      if (direct) tb.g_map[d.gval] = (uint16_t)g;
+      if (direct && g < a.n_groups) tb.g_map[d.gval] = (uint16_t)g;
     }
   }
   __syncthreads();
 }
 
-__device__ __forceinline__ void load_queries(const JoinArgs& a, uint32_t q0, uint32_t (&ql)[kQPT],
+// Loads the 4 consecutive VIRTUAL queries v0..v0+3 of a lane. With one length class a virtual query is
+// the query itself (128-bit loads); with n_comp slots, v = q * n_comp + slot, so a lane holds all the
+// slots of its 4 / n_comp queries (v0 is a multiple of 4 and n_comp is 1, 2 or 4).
+__device__ __forceinline__ void load_queries(const JoinArgs& a, uint32_t v0, uint32_t (&ql)[kQPT],
                                              uint32_t (&qh)[kQPT], uint32_t (&qg)[kQPT]) {
-  if (a.vec_ok && q0 + kQPT <= a.n_q) {
-    uint4 t = *reinterpret_cast<const uint4*>(a.qlow + q0);
+  if (a.n_comp == 1 && a.vec_ok && v0 + kQPT <= a.n_q) {
+    uint4 t = *reinterpret_cast<const uint4*>(a.qlow + v0);
     ql[0] = t.x; ql[1] = t.y; ql[2] = t.z; ql[3] = t.w;
-    t = *reinterpret_cast<const uint4*>(a.qhigh + q0);
+    t = *reinterpret_cast<const uint4*>(a.qhigh + v0);
     qh[0] = t.x; qh[1] = t.y; qh[2] = t.z; qh[3] = t.w;
     if (a.qgroup) {
-      t = *reinterpret_cast<const uint4*>(a.qgroup + q0);
+      t = *reinterpret_cast<const uint4*>(a.qgroup + v0);
       qg[0] = t.x; qg[1] = t.y; qg[2] = t.z; qg[3] = t.w;
     } else {
       qg[0] = qg[1] = qg[2] = qg[3] = 0u;
@@ -153,19 +160,21 @@ __device__ __forceinline__ void load_queries(const JoinArgs& a, uint32_t q0, uin
   } else {
 #pragma unroll
     for (int j = 0; j < kQPT; ++j) {
-      bool v = q0 + j < a.n_q;  // q0 may be past the end when prefetching
-      ql[j] = v ? a.qlow[q0 + j] : 0u;
-      qh[j] = v ? a.qhigh[q0 + j] : 0u;
-      qg[j] = (v && a.qgroup) ? a.qgroup[q0 + j] : 0u;
+      const uint32_t v = v0 + j;
+      const uint32_t q = v >> a.comp_shift;
+      const bool ok = v >= v0 && q < a.n_q;  // v0 may be past the end (or wrap) when prefetching
+      ql[j] = ok ? a.qlow[q] : 0u;
+      qh[j] = ok ? a.qhigh[q] : 0u;
+      qg[j] = (ok && a.qgroup) ? a.qgroup[q] : 0u;
     }
   }
 }
 
 // K3 step 1: candidate row range [lb, lb+len) of one query. `valid` = the query exists.
 __device__ __forceinline__ void query_bounds(const JoinArgs& a, const GroupTables& tb, bool valid,
-                                             uint32_t ql, uint32_t qh, uint32_t qg, uint32_t& lb,
-                                             uint32_t& len, uint32_t& inline_mask) {
-  const bool in_smem = a.n_groups <= (uint32_t)kMaxSmemGroups;
+                                             uint32_t slot, uint32_t ql, uint32_t qh, uint32_t qg,
+                                             uint32_t& lb, uint32_t& len, uint32_t& inline_mask) {
+  const bool in_smem = a.n_groups * a.n_comp <= (uint32_t)kMaxSmemGroups;
   const bool direct = in_smem && a.max_gval < (uint32_t)kDirectGroups;
   lb = 0;
   len = 0;
@@ -174,22 +183,30 @@ __device__ __forceinline__ void query_bounds(const JoinArgs& a, const GroupTable
   uint64_t bin_base = 0;
   if (valid) {
     if (direct) {
-      const uint32_t gi = qg < (uint32_t)kDirectGroups ? tb.g_map[qg] : 0xffffu;
-      if (gi != 0xffffu) { nb = tb.g_nb[gi]; bin_base = tb.g_base[gi]; }
+      uint32_t gi = qg < (uint32_t)kDirectGroups ? tb.g_map[qg] : 0xffffu;
+      if (gi != 0xffffu) { gi += slot * a.n_groups; nb = tb.g_nb[gi]; bin_base = tb.g_base[gi]; }
     } else if (in_smem) {
       uint32_t lo = 0, hi = a.n_groups;
       while (lo < hi) {
         uint32_t mid = (lo + hi) >> 1;
         if (tb.g_val[mid] < qg) lo = mid + 1; else hi = mid;
       }
-      if (lo < a.n_groups && tb.g_val[lo] == qg) { nb = tb.g_nb[lo]; bin_base = tb.g_base[lo]; }
+      if (lo < a.n_groups && tb.g_val[lo] == qg) {
+        lo += slot * a.n_groups;
+        nb = tb.g_nb[lo];
+        bin_base = tb.g_base[lo];
+      }
     } else {
       uint32_t lo = 0, hi = a.n_groups;
       while (lo < hi) {
         uint32_t mid = (lo + hi) >> 1;
         if (a.groups[mid].gval < qg) lo = mid + 1; else hi = mid;
       }
-      if (lo < a.n_groups && a.groups[lo].gval == qg) { nb = a.groups[lo].nb; bin_base = a.groups[lo].bin_base; }
+      if (lo < a.n_groups && a.groups[lo].gval == qg) {
+        lo += slot * a.n_groups;
+        nb = a.groups[lo].nb;
+        bin_base = a.groups[lo].bin_base;
+      }
     }
   }
   const uint32_t b_lo = ql >> a.shift;
@@ -242,6 +259,8 @@ struct LongCtx {  // what the long-range path needs, passed BY VALUE into the ou
   uint32_t* hit_target;
   uint32_t* hit_query;
   uint64_t capacity;
+  uint32_t qid_base;
+  uint32_t comp_shift;
 };
 
 struct LongRange {
@@ -358,7 +377,7 @@ __device__ __forceinline__ void scan_two_long(const LongCtx& c, int lane, const 
 template <bool EMIT>
 __device__ __noinline__ uint4 long_ranges(LongCtx c, int lane, uint32_t bigbits, uint4 lb4, uint4 ub4,
                                           uint4 ql4, uint4 cnt4, uint64_t pos_0, uint64_t pos_1,
-                                          uint64_t pos_2, uint64_t pos_3, uint32_t qid0) {
+                                          uint64_t pos_2, uint64_t pos_3, uint32_t vq0) {
   const uint32_t lb[kQPT] = {lb4.x, lb4.y, lb4.z, lb4.w};
   const uint32_t ub[kQPT] = {ub4.x, ub4.y, ub4.z, ub4.w};
   const uint32_t ql[kQPT] = {ql4.x, ql4.y, ql4.z, ql4.w};
@@ -377,7 +396,8 @@ __device__ __noinline__ uint4 long_ranges(LongCtx c, int lane, uint32_t bigbits,
       A.lb = __shfl_sync(0xffffffffu, lb[j], sa); B.lb = __shfl_sync(0xffffffffu, lb[j], sb);
       A.ub = __shfl_sync(0xffffffffu, ub[j], sa); B.ub = __shfl_sync(0xffffffffu, ub[j], sb);
       A.ql = __shfl_sync(0xffffffffu, ql[j], sa); B.ql = __shfl_sync(0xffffffffu, ql[j], sb);
-      A.qid = qid0 + (uint32_t)sa * kQPT + j;       B.qid = qid0 + (uint32_t)sb * kQPT + j;
+      A.qid = c.qid_base + ((vq0 + (uint32_t)sa * kQPT + j) >> c.comp_shift);  // vq0 = warp's first virtual query
+      B.qid = c.qid_base + ((vq0 + (uint32_t)sb * kQPT + j) >> c.comp_shift);
       A.cnt = B.cnt = 0;
       A.base = B.base = 0;
       if (EMIT) {
@@ -402,6 +422,8 @@ __device__ __forceinline__ LongCtx long_ctx(const JoinArgs& a) {
   c.hit_target = a.hit_target;
   c.hit_query = a.hit_query;
   c.capacity = a.capacity;
+  c.qid_base = a.qid_base;
+  c.comp_shift = a.comp_shift;
   return c;
 }
 __device__ __forceinline__ uint32_t pack_bits(const bool (&b)[kQPT]) {
@@ -415,7 +437,7 @@ __device__ __forceinline__ uint32_t pack_bits(const bool (&b)[kQPT]) {
 template <bool GAPS>
 __device__ __forceinline__ void emit_short(const JoinArgs& a, StageBuffers& st, int warp, int lane,
                                            const uint32_t (&mask)[kQPT], const uint32_t (&lb)[kQPT],
-                                           const uint64_t (&off)[kQPT], uint64_t base, uint32_t qid0) {
+                                           const uint64_t (&off)[kQPT], uint64_t base, uint32_t vq0) {
   const uint32_t lane_hits = __popc(mask[0]) + __popc(mask[1]) + __popc(mask[2]) + __popc(mask[3]);
   uint32_t incl = lane_hits;
 #pragma unroll
@@ -460,7 +482,7 @@ __device__ __forceinline__ void emit_short(const JoinArgs& a, StageBuffers& st, 
       const uint64_t pos = base + (GAPS ? st.pos[warp][s] : (uint64_t)(r0 + s));
       if (pos < a.capacity) {
         a.hit_target[pos] = a.ids[v.x];
-        a.hit_query[pos] = qid0 + v.y;
+        a.hit_query[pos] = a.qid_base + ((vq0 + v.y) >> a.comp_shift);
       }
     }
     __syncwarp();
@@ -476,7 +498,7 @@ __global__ void __launch_bounds__(kJoinThreads, kProbeMinBlocks) probe_kernel(co
   load_group_tables(a, tb);
 
   const uint64_t chunk_begin = (uint64_t)blockIdx.x * a.chunk;
-  const uint64_t chunk_end = min(chunk_begin + (uint64_t)a.chunk, (uint64_t)a.n_q);
+  const uint64_t chunk_end = min(chunk_begin + (uint64_t)a.chunk, (uint64_t)a.n_vq);
   uint64_t acc = 0;  // hits of this lane's queries over the whole chunk
 
   uint64_t w0 = chunk_begin + (uint64_t)warp * kWarpTile;
@@ -491,7 +513,8 @@ __global__ void __launch_bounds__(kJoinThreads, kProbeMinBlocks) probe_kernel(co
 
     uint32_t lb[kQPT], len[kQPT], w[kQPT];
 #pragma unroll
-    for (int j = 0; j < kQPT; ++j) query_bounds(a, tb, q0 + j < a.n_q, ql[j], qh[j], qg[j], lb[j], len[j], w[j]);
+    for (int j = 0; j < kQPT; ++j)
+      query_bounds(a, tb, q0 + j < a.n_vq, (q0 + j) & (a.n_comp - 1u), ql[j], qh[j], qg[j], lb[j], len[j], w[j]);
     scan_short(a, ql, qh, lb, len, w);
     bool big[kQPT];
     uint32_t ub[kQPT];
@@ -553,7 +576,7 @@ __global__ void __launch_bounds__(kJoinThreads, kEmitMinBlocks) emit_kernel(cons
   for (int w = 0; w < kJoinWarps; ++w) running += s_red[w];
 
   const uint64_t chunk_begin = (uint64_t)blockIdx.x * a.chunk;
-  const uint64_t chunk_end = min(chunk_begin + (uint64_t)a.chunk, (uint64_t)a.n_q);
+  const uint64_t chunk_end = min(chunk_begin + (uint64_t)a.chunk, (uint64_t)a.n_vq);
   if (blockIdx.x == gridDim.x - 1 && tid == 0) {  // grand total
     const uint64_t t = running + a.cta_total[blockIdx.x];
     a.offsets[a.n_q] = t;
@@ -614,20 +637,23 @@ __global__ void __launch_bounds__(kJoinThreads, kEmitMinBlocks) emit_kernel(cons
 #pragma unroll
       for (int j = 0; j < kQPT; ++j) { off[j] = run; run += cnt[j]; }
     }
-    if (a.vec_ok && q0 + kQPT <= a.n_q) {
+    if (a.n_comp == 1 && a.vec_ok && q0 + kQPT <= a.n_q) {
       ulonglong2* o = reinterpret_cast<ulonglong2*>(a.offsets + q0);
       o[0] = make_ulonglong2(warp_base + off[0], warp_base + off[1]);
       o[1] = make_ulonglong2(warp_base + off[2], warp_base + off[3]);
-    } else {
+    } else {  // the CSR offset of a query is the position of its FIRST slot's first hit
 #pragma unroll
-      for (int j = 0; j < kQPT; ++j) if (q0 + j < a.n_q) a.offsets[q0 + j] = warp_base + off[j];
+      for (int j = 0; j < kQPT; ++j) {
+        const uint32_t v = q0 + j;
+        if ((v & (a.n_comp - 1u)) == 0 && v < a.n_vq) a.offsets[v >> a.comp_shift] = warp_base + off[j];
+      }
     }
     if (!EMIT) continue;
 
     // ---- scatter ------------------------------------------------------------------------------------
     const bool warp_big = __any_sync(0xffffffffu, lane_big);
-    if (warp_big) emit_short<true>(a, st, warp, lane, mask, lb, off, warp_base, a.qid_base + w0);
-    else emit_short<false>(a, st, warp, lane, mask, lb, off, warp_base, a.qid_base + w0);
+    if (warp_big) emit_short<true>(a, st, warp, lane, mask, lb, off, warp_base, w0);
+    else emit_short<false>(a, st, warp, lane, mask, lb, off, warp_base, w0);
     seen_big |= warp_big;
   }
   if (!EMIT || !seen_big) return;
@@ -646,19 +672,22 @@ __global__ void __launch_bounds__(kJoinThreads, kEmitMinBlocks) emit_kernel(cons
     uint32_t ql[kQPT], blb[kQPT], bub[kQPT], cnt[kQPT];
     uint64_t pos[kQPT];
     bool big[kQPT];
+    uint64_t run = 0;  // hits of the earlier slots of the same query (all slots of a query sit in one lane)
 #pragma unroll
     for (int j = 0; j < kQPT; ++j) {
+      const uint32_t v = q0 + j;
       big[j] = (w[j] & kBigFlag) != 0;
-      cnt[j] = w[j] & ~kBigFlag;
-      ql[j] = big[j] ? a.qlow[q0 + j] : 0u;
-      blb[j] = big[j] ? a.st_lb[q0 + j] : 0u;
-      bub[j] = big[j] ? a.st_ub[q0 + j] : 0u;
-      pos[j] = big[j] ? a.offsets[q0 + j] : 0ull;
+      cnt[j] = big[j] ? (w[j] & ~kBigFlag) : (uint32_t)__popc(w[j]);
+      if ((v & (a.n_comp - 1u)) == 0) run = 0;
+      ql[j] = big[j] ? a.qlow[v >> a.comp_shift] : 0u;
+      blb[j] = big[j] ? a.st_lb[v] : 0u;
+      bub[j] = big[j] ? a.st_ub[v] : 0u;
+      pos[j] = big[j] ? a.offsets[v >> a.comp_shift] + run : 0ull;
+      run += cnt[j];
     }
     long_ranges<true>(long_ctx(a), lane, pack_bits(big), make_uint4(blb[0], blb[1], blb[2], blb[3]),
                       make_uint4(bub[0], bub[1], bub[2], bub[3]), make_uint4(ql[0], ql[1], ql[2], ql[3]),
-                      make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]), pos[0], pos[1], pos[2], pos[3],
-                      a.qid_base + w0);
+                      make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]), pos[0], pos[1], pos[2], pos[3], w0);
   }
 }
 
@@ -670,14 +699,15 @@ __global__ void __launch_bounds__(kJoinThreads, kJoinMinBlocks) direct_kernel(co
   __shared__ StageBuffers st;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   load_group_tables(a, tb);
-  const uint32_t n_tiles = (a.n_q + kCtaTile - 1) / kCtaTile;
+  const uint32_t n_tiles = (uint32_t)(((uint64_t)a.n_vq + kCtaTile - 1) / kCtaTile);
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint32_t w0 = tile * (uint32_t)kCtaTile + (uint32_t)warp * kWarpTile;
     const uint32_t q0 = w0 + (uint32_t)lane * kQPT;
     uint32_t ql[kQPT], qh[kQPT], qg[kQPT], lb[kQPT], len[kQPT], mask[kQPT];
     load_queries(a, q0, ql, qh, qg);
 #pragma unroll
-    for (int j = 0; j < kQPT; ++j) query_bounds(a, tb, q0 + j < a.n_q, ql[j], qh[j], qg[j], lb[j], len[j], mask[j]);
+    for (int j = 0; j < kQPT; ++j)
+      query_bounds(a, tb, q0 + j < a.n_vq, (q0 + j) & (a.n_comp - 1u), ql[j], qh[j], qg[j], lb[j], len[j], mask[j]);
     scan_short(a, ql, qh, lb, len, mask);
     bool big[kQPT];
     uint32_t ub[kQPT], cnt[kQPT];
@@ -690,35 +720,43 @@ __global__ void __launch_bounds__(kJoinThreads, kJoinMinBlocks) direct_kernel(co
       cnt[j] = __popc(mask[j]);
     }
     const bool warp_big = __any_sync(0xffffffffu, lane_big);
-    if (MODE == kModeAny) {
-      if (warp_big) {
-        const uint4 c4 = long_ranges<false>(long_ctx(a), lane, pack_bits(big), make_uint4(lb[0], lb[1], lb[2], lb[3]),
-                                            make_uint4(ub[0], ub[1], ub[2], ub[3]),
-                                            make_uint4(ql[0], ql[1], ql[2], ql[3]), make_uint4(0, 0, 0, 0), 0,
-                                            0, 0, 0, 0);
-        const uint32_t cl[kQPT] = {c4.x, c4.y, c4.z, c4.w};
-#pragma unroll
-        for (int j = 0; j < kQPT; ++j)
-          if (big[j]) cnt[j] = cl[j];
-      }
+    if (warp_big) {  // hit counts of the long ranges (the caller's offsets only give per-query totals)
+      const uint4 c4 = long_ranges<false>(long_ctx(a), lane, pack_bits(big), make_uint4(lb[0], lb[1], lb[2], lb[3]),
+                                          make_uint4(ub[0], ub[1], ub[2], ub[3]),
+                                          make_uint4(ql[0], ql[1], ql[2], ql[3]), make_uint4(0, 0, 0, 0), 0, 0,
+                                          0, 0, 0);
+      const uint32_t cl[kQPT] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
       for (int j = 0; j < kQPT; ++j)
-        if (q0 + j < a.n_q) a.any[q0 + j] = cnt[j] ? 1 : 0;
+        if (big[j]) cnt[j] = cl[j];
+    }
+    if (MODE == kModeAny) {  // OR over the slots of a query (they sit in one lane)
+      uint32_t acc = 0;
+#pragma unroll
+      for (int j = kQPT - 1; j >= 0; --j) {
+        const uint32_t v = q0 + j;
+        acc |= cnt[j];
+        if ((v & (a.n_comp - 1u)) == 0) {
+          if (v < a.n_vq) a.any[v >> a.comp_shift] = acc ? 1 : 0;
+          acc = 0;
+        }
+      }
       continue;
     }
     uint64_t off[kQPT];
+    uint64_t run = 0;
 #pragma unroll
-    for (int j = 0; j < kQPT; ++j) {
-      off[j] = (q0 + j < a.n_q) ? a.offsets[q0 + j] : 0ull;
-      // hits of a long range = next offset - this offset (the caller's offsets come from the count call)
-      if (big[j]) cnt[j] = (uint32_t)(a.offsets[q0 + j + 1] - off[j]);
+    for (int j = 0; j < kQPT; ++j) {  // slot s of a query starts after the hits of its slots < s
+      const uint32_t v = q0 + j;
+      if ((v & (a.n_comp - 1u)) == 0) run = 0;
+      off[j] = (v < a.n_vq) ? a.offsets[v >> a.comp_shift] + run : 0ull;
+      run += cnt[j];
     }
-    emit_short<true>(a, st, warp, lane, mask, lb, off, 0, a.qid_base + w0);
+    emit_short<true>(a, st, warp, lane, mask, lb, off, 0, w0);
     if (warp_big)
       long_ranges<true>(long_ctx(a), lane, pack_bits(big), make_uint4(lb[0], lb[1], lb[2], lb[3]),
                         make_uint4(ub[0], ub[1], ub[2], ub[3]), make_uint4(ql[0], ql[1], ql[2], ql[3]),
-                        make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]), off[0], off[1], off[2], off[3],
-                        a.qid_base + w0);
+                        make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]), off[0], off[1], off[2], off[3], w0);
   }
 }
 
@@ -768,6 +806,11 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
   a.qlow = d_qlow;
   a.qhigh = d_qhigh;
   a.n_q = (uint32_t)n_q;
+  a.n_comp = ix->n_comp;
+  a.comp_shift = ix->n_comp == 4 ? 2u : (ix->n_comp == 2 ? 1u : 0u);
+  const uint64_t n_vq = n_q * ix->n_comp;  // virtual queries: one per (query, length-class slot)
+  if (n_vq > 0xfffffffeull) { set_error("query batch x length classes exceeds 2^32-2"); return BCU_E_LIMIT; }
+  a.n_vq = (uint32_t)n_vq;
   a.chunk = 0;
   a.vec_ok = aligned16(d_qlow) && aligned16(d_qhigh) && (!d_qgroup || aligned16(d_qgroup)) &&
              (!d_offsets || aligned16(d_offsets));
@@ -783,7 +826,7 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
   a.st_ub = nullptr;
   a.cta_total = nullptr;
   a.base_in = d_offset_base;
-  const uint64_t n_tiles = (n_q + kCtaTile - 1) / kCtaTile;
+  const uint64_t n_tiles = (n_vq + kCtaTile - 1) / kCtaTile;
   const uint64_t cta_budget = (uint64_t)sm_count(ix->device) * kJoinMinBlocks * 2;  // two waves of CTAs
   if (!prefix) {
     const unsigned grid = (unsigned)(n_tiles < cta_budget ? n_tiles : cta_budget);

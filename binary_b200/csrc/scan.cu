@@ -1,7 +1,8 @@
 // Device-wide single-pass scans built on lookback.cuh:
 //   exclusive_sum_u32      -- digit-histogram prefix sums for the radix sort (K1)
 //   segmented_running_max  -- the "running max-end" array of the flat index (K2): for each sorted row
-//                             the max of `high` over the rows of the same group up to and including it
+//                             the max of `high` over the rows of the same segment (component, group) up to
+//                             and including it
 // HBM roofline: 1 read + 1 write of the array (4 B + 4 B per element).
 #include "common.cuh"
 #include "lookback.cuh"
@@ -62,15 +63,15 @@ __global__ void __launch_bounds__(kScanThreads)
   const uint32_t tile = s_tile;
   const uint64_t base = (uint64_t)tile * kScanTile + (uint64_t)threadIdx.x * kScanItems;
   uint64_t e[kScanItems];  // SegMaxOp elements: head flag in bit 32, value in the low word
-  uint32_t prev_group = 0;
-  if (base > 0 && base < n) prev_group = (uint32_t)(keys[base - 1] >> 32);
+  uint64_t prev_seg = 0;
+  if (base > 0 && base < n) prev_seg = keys[base - 1];
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k) {
     if (base + k < n) {
-      uint32_t g = (uint32_t)(keys[base + k] >> 32);
-      bool head = (base + k == 0) || (g != prev_group);
+      uint64_t g = keys[base + k];  // segment key: rows of one segment carry the same value
+      bool head = (base + k == 0) || (g != prev_seg);
       e[k] = ((uint64_t)head << 32) | val[base + k];
-      prev_group = g;
+      prev_seg = g;
     } else {
       e[k] = SegMaxOp::identity();
     }

@@ -222,3 +222,33 @@ def test_sharded_join_on_gpu(port_oracle):
     assert np.array_equal(off, want_off)
     assert np.array_equal(hq, np.repeat(np.arange(c["ql"].size, dtype=np.uint32), np.diff(want_off).astype(np.int64)))
     assert np.array_equal(canonical(off, ht)[1], want_tid)
+
+
+def test_length_classes_keep_giant_intervals_from_poisoning_the_index(port_oracle):
+    """The classic AIList problem: a few chromosome-sized targets among many short ones
+    would drag the running max-end along and make every later query scan from them. The build splits
+    targets into length classes; results must not change and the index must report > 1 class."""
+    rng = np.random.default_rng(99)
+    n_t, n_q = 200_000, 100_000
+    tl = rng.integers(0, 100_000_000, n_t).astype(np.uint32)
+    th = (tl + rng.integers(10, 3000, n_t)).astype(np.uint32)
+    tl[:6] = [5, 1000, 2_000_000, 40_000_000, 0, 70_000_000]
+    th[:6] = [99_000_000, 60_000_000, 99_999_999, 41_000_000, 100_000_000, 70_050_000]
+    tg = (rng.integers(0, 3, n_t)).astype(np.uint32)
+    ql = rng.integers(0, 100_000_000, n_q).astype(np.uint32)
+    qh = (ql + rng.integers(0, 500, n_q)).astype(np.uint32)
+    qg = (rng.integers(0, 4, n_q)).astype(np.uint32)
+    ix = DeviceIndex.build(tl, th, tg)
+    assert ix.info()["n_components"] > 1
+    c = dict(tl=tl, th=th, tg=tg, ql=ql, qh=qh, qg=qg)
+    _check_all_entry_points(c, port_oracle)
+    # and with the decomposition switched off the answer is the same (results never depend on it)
+    os.environ["BCU_MAX_CLASSES"] = "1"
+    try:
+        ix1 = DeviceIndex.build(tl, th, tg)
+        assert ix1.info()["n_components"] == 1
+        off1, _, ht1 = ix1.join(ql[:2000], qh[:2000], qg[:2000])
+    finally:
+        del os.environ["BCU_MAX_CLASSES"]
+    off, _, ht = ix.join(ql[:2000], qh[:2000], qg[:2000])
+    assert np.array_equal(off, off1) and np.array_equal(canonical(off, ht)[1], canonical(off1, ht1)[1])
