@@ -204,12 +204,14 @@ def run_ours(args):
                                stream=stream)
     torch.cuda.synchronize()
     build_ms_first = (time.perf_counter() - tb) * 1e3
-    tb = time.perf_counter()
-    ix2 = DeviceIndex.build_dev(n_t, d_tl.data_ptr(), d_th.data_ptr(), d_tg.data_ptr(), device=local,
-                                stream=stream)
-    torch.cuda.synchronize()
-    build_ms = (time.perf_counter() - tb) * 1e3
-    ix2.close()
+    build_ms = None
+    for _ in range(2):  # steady-state rebuild: the second one reuses the pool memory of the first
+        tb = time.perf_counter()
+        ix2 = DeviceIndex.build_dev(n_t, d_tl.data_ptr(), d_th.data_ptr(), d_tg.data_ptr(), device=local,
+                                    stream=stream)
+        torch.cuda.synchronize()
+        build_ms = (time.perf_counter() - tb) * 1e3
+        ix2.close()
     info = ix.info()
 
     # ---- output buffers: size the pair buffer with one count pass ----
