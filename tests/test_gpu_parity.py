@@ -252,3 +252,24 @@ def test_length_classes_keep_giant_intervals_from_poisoning_the_index(port_oracl
         del os.environ["BCU_MAX_CLASSES"]
     off, _, ht = ix.join(ql[:2000], qh[:2000], qg[:2000])
     assert np.array_equal(off, off1) and np.array_equal(canonical(off, ht)[1], canonical(off1, ht1)[1])
+
+
+@pytest.mark.parametrize("label,groups", [
+    ("sparse-ids-smem-bsearch", [7, 5000, 70000, 2**31, 2**32 - 1]),       # <=256 groups, values >= 1024
+    ("many-groups-global-table", list(range(0, 3000, 3))),                  # 1000 groups: descriptors in global memory
+])
+def test_group_lookup_modes(port_oracle, label, groups):
+    """The three group-lookup paths of join.cu (direct map / shared-memory binary search / global table),
+    with and without length classes, plus queries for groups that have no target."""
+    rng = np.random.default_rng(len(groups))
+    n_t, n_q = 30000, 20000
+    gv = np.array(groups, dtype=np.uint64)
+    tg = gv[rng.integers(0, gv.size, n_t)].astype(np.uint32)
+    tl = rng.integers(0, 500_000, n_t).astype(np.uint32)
+    th = (tl + rng.integers(0, 400, n_t)).astype(np.uint32)
+    th[:20] = tl[:20] + 300_000                                              # a few giants -> length classes
+    qpool = np.concatenate([gv, np.array([1, 4999, 123456789], dtype=np.uint64)])   # unknown groups too
+    qg = qpool[rng.integers(0, qpool.size, n_q)].astype(np.uint32)
+    ql = rng.integers(0, 500_000, n_q).astype(np.uint32)
+    qh = (ql + rng.integers(0, 300, n_q)).astype(np.uint32)
+    _check_all_entry_points(dict(tl=tl, th=th, tg=tg, ql=ql, qh=qh, qg=qg), port_oracle)
