@@ -114,7 +114,7 @@ extern "C" int bcu_join_dev(const bcu_index* ix, uint64_t n_q, const uint32_t* d
                             uint64_t pair_capacity, uint32_t* d_hit_query, uint32_t* d_hit_target,
                             uint64_t* d_total, uint32_t query_id_base, void* stream) {
   BCU_TRY(check_query_args("bcu_join_dev", ix, n_q, d_qlow, d_qhigh));
-  if (!d_offsets || (pair_capacity && (!d_hit_query || !d_hit_target))) {
+  if (!d_offsets || (pair_capacity && !d_hit_target)) {
     set_error("bcu_join_dev: NULL output pointer");
     return BCU_E_INVALID;
   }

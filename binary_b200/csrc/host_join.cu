@@ -5,6 +5,7 @@
 // chunk's emit kernel starts from the previous chunk's running total, which stays on the device.
 // Device staging buffers and streams are cached per host thread and device (grow-only; bcu_trim frees).
 #include <algorithm>
+#include <cstdlib>
 #include <memory>
 #include <vector>
 
@@ -12,7 +13,7 @@
 
 namespace bcu {
 
-constexpr uint64_t kHostChunk = 2u << 20;  // queries per pipeline chunk (multiple of the CTA step)
+constexpr uint64_t kHostChunkDefault = 2u << 20;  // queries per pipeline chunk (multiple of the CTA step)
 constexpr int kMaxDevices = 64;
 
 struct HostCtx {
@@ -59,7 +60,8 @@ struct HostCtx {
     return BCU_OK;
   }
 
-  int prepare(int dev, uint64_t n_q, uint64_t pair_capacity, uint64_t n_chunks, bool has_group) {
+  int prepare(int dev, uint64_t n_q, uint64_t pair_capacity, uint64_t n_chunks, bool has_group,
+              bool want_query_ids) {
     device = dev;
     if (!s_in) {
       BCU_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
@@ -70,7 +72,7 @@ struct HostCtx {
     BCU_TRY(grow(&d_ql, &cap_ql, n_q));
     BCU_TRY(grow(&d_qh, &cap_qh, n_q));
     BCU_TRY(grow(&d_off, &cap_off, n_q + 1));
-    BCU_TRY(grow(&d_hq, &cap_hq, pair_capacity));
+    if (want_query_ids) BCU_TRY(grow(&d_hq, &cap_hq, pair_capacity));
     BCU_TRY(grow(&d_ht, &cap_ht, pair_capacity));
     if (n_chunks > cap_chunks) {
       cudaFree(d_totals);
@@ -91,6 +93,17 @@ struct HostCtx {
     return BCU_OK;
   }
 };
+
+// BCU_HOST_CHUNK (queries, rounded to a multiple of 1024) overrides the pipeline granularity
+static uint64_t host_chunk() {
+  static const uint64_t v = [] {
+    const char* e = std::getenv("BCU_HOST_CHUNK");
+    uint64_t c = e ? std::strtoull(e, nullptr, 10) : 0;
+    if (c < 1024) c = kHostChunkDefault;
+    return (c + 1023) / 1024 * 1024;
+  }();
+  return v;
+}
 
 static HostCtx* host_ctx(int device) {
   static thread_local std::unique_ptr<HostCtx> ctx[kMaxDevices];
@@ -125,8 +138,8 @@ extern "C" int bcu_join(const bcu_index* ix, uint64_t n_q, const uint32_t* qgrou
   if (n_q && (!qlow || !qhigh)) { set_error("bcu_join: qlow/qhigh are NULL"); return BCU_E_INVALID; }
   if (n_q > 0xfffffffeull) { set_error("bcu_join: n_q exceeds 2^32-2"); return BCU_E_LIMIT; }
   if (!offsets || !total) { set_error("bcu_join: offsets/total are NULL"); return BCU_E_INVALID; }
-  if (pair_capacity && (!hit_query || !hit_target)) {
-    set_error("bcu_join: pair buffers are NULL");
+  if (pair_capacity && !hit_target) {
+    set_error("bcu_join: hit_target is NULL");
     return BCU_E_INVALID;
   }
   *total = 0;
@@ -138,19 +151,29 @@ extern "C" int bcu_join(const bcu_index* ix, uint64_t n_q, const uint32_t* qgrou
   if (!guard.ok) { set_error("bcu_join: cannot select CUDA device %d", ix->device); return BCU_E_CUDA; }
   HostCtx* c = host_ctx(ix->device);
   if (!c) { set_error("bcu_join: host context allocation failed"); return BCU_E_NOMEM; }
-  const uint64_t n_chunks = (n_q + kHostChunk - 1) / kHostChunk;
-  BCU_TRY(c->prepare(ix->device, n_q, pair_capacity, n_chunks, qgroup != nullptr));
+  // chunk boundaries: the first two chunks are a quarter and a half of the steady size so that the
+  // copy-out stream starts early (the pipeline's fill and drain are what is not overlapped)
+  const uint64_t kHostChunk = host_chunk();
+  std::vector<uint64_t> bounds{0};
+  for (uint64_t step : {kHostChunk / 4, kHostChunk / 2}) {
+    step = std::max<uint64_t>(step / 1024 * 1024, 1024);
+    if (bounds.back() + step < n_q) bounds.push_back(bounds.back() + step);
+  }
+  while (bounds.back() + kHostChunk < n_q) bounds.push_back(bounds.back() + kHostChunk);
+  bounds.push_back(n_q);
+  const uint64_t n_chunks = bounds.size() - 1;
+  BCU_TRY(c->prepare(ix->device, n_q, pair_capacity, n_chunks, qgroup != nullptr, hit_query != nullptr));
 
   // 1. queue every chunk's H2D copies and kernels; nothing here blocks the host
   for (uint64_t i = 0; i < n_chunks; ++i) {
-    const uint64_t b = i * kHostChunk, n = std::min(kHostChunk, n_q - b);
+    const uint64_t b = bounds[i], n = bounds[i + 1] - b;
     if (qgroup) BCU_CUDA(cudaMemcpyAsync(c->d_qg + b, qgroup + b, n * 4, cudaMemcpyHostToDevice, c->s_in));
     BCU_CUDA(cudaMemcpyAsync(c->d_ql + b, qlow + b, n * 4, cudaMemcpyHostToDevice, c->s_in));
     BCU_CUDA(cudaMemcpyAsync(c->d_qh + b, qhigh + b, n * 4, cudaMemcpyHostToDevice, c->s_in));
     BCU_CUDA(cudaEventRecord(c->ev_in[i], c->s_in));
     BCU_CUDA(cudaStreamWaitEvent(c->s_run, c->ev_in[i], 0));
     BCU_TRY(launch_join(ix, kModeFused, n, qgroup ? c->d_qg + b : nullptr, c->d_ql + b, c->d_qh + b,
-                        c->d_off + b, pair_capacity, c->d_hq, c->d_ht, c->d_totals + i, nullptr,
+                        c->d_off + b, pair_capacity, hit_query ? c->d_hq : nullptr, c->d_ht, c->d_totals + i, nullptr,
                         (uint32_t)b, c->s_run, i ? c->d_totals + (i - 1) : nullptr));
     BCU_CUDA(cudaMemcpyAsync(c->h_totals + i, c->d_totals + i, 8, cudaMemcpyDeviceToHost, c->s_run));
     BCU_CUDA(cudaEventRecord(c->ev_run[i], c->s_run));
@@ -158,7 +181,7 @@ extern "C" int bcu_join(const bcu_index* ix, uint64_t n_q, const uint32_t* qgrou
   // 2. as each chunk finishes, its running total tells how many pairs to bring back
   uint64_t done_pairs = 0;
   for (uint64_t i = 0; i < n_chunks; ++i) {
-    const uint64_t b = i * kHostChunk, n = std::min(kHostChunk, n_q - b);
+    const uint64_t b = bounds[i], n = bounds[i + 1] - b;
     BCU_CUDA(cudaEventSynchronize(c->ev_run[i]));
     const uint64_t t = c->h_totals[i];
     BCU_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_run[i], 0));
@@ -166,8 +189,9 @@ extern "C" int bcu_join(const bcu_index* ix, uint64_t n_q, const uint32_t* qgrou
     BCU_CUDA(cudaMemcpyAsync(offsets + b, c->d_off + b, n_off * 8, cudaMemcpyDeviceToHost, c->s_out));
     const uint64_t upto = std::min(t, pair_capacity);
     if (upto > done_pairs) {
-      BCU_CUDA(cudaMemcpyAsync(hit_query + done_pairs, c->d_hq + done_pairs, (upto - done_pairs) * 4,
-                               cudaMemcpyDeviceToHost, c->s_out));
+      if (hit_query)
+        BCU_CUDA(cudaMemcpyAsync(hit_query + done_pairs, c->d_hq + done_pairs, (upto - done_pairs) * 4,
+                                 cudaMemcpyDeviceToHost, c->s_out));
       BCU_CUDA(cudaMemcpyAsync(hit_target + done_pairs, c->d_ht + done_pairs, (upto - done_pairs) * 4,
                                cudaMemcpyDeviceToHost, c->s_out));
       done_pairs = upto;

@@ -360,6 +360,7 @@ __device__ __forceinline__ void scan_two_long(const LongCtx& c, int lane, const 
     cnt_b = cb;
   } else {
     // query-id column: one value per range, coalesced fill
+    if (!c.hit_query) return;  // the caller does not want the (redundant with the offsets) query-id column
     uint32_t* qa = c.hit_query + A.base;
     const uint32_t na = min(A.cnt, lim_a);
     for (uint32_t k = lane; k < na; k += 32) qa[k] = A.qid;
@@ -482,7 +483,7 @@ __device__ __forceinline__ void emit_short(const JoinArgs& a, StageBuffers& st, 
       const uint64_t pos = base + (GAPS ? st.pos[warp][s] : (uint64_t)(r0 + s));
       if (pos < a.capacity) {
         a.hit_target[pos] = a.ids[v.x];
-        a.hit_query[pos] = a.qid_base + ((vq0 + v.y) >> a.comp_shift);
+        if (a.hit_query) a.hit_query[pos] = a.qid_base + ((vq0 + v.y) >> a.comp_shift);
       }
     }
     __syncwarp();

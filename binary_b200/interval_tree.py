@@ -114,10 +114,12 @@ class DeviceIndex:
                                             offsets.ctypes.data, hq.ctypes.data, ht.ctypes.data))
         return hq, ht
 
-    def join(self, qlow, qhigh, qgroup=None, pair_capacity: Optional[int] = None):
-        """(offsets, hit_query, hit_target) in one fused pass -- ``bcu_join``.
+    def join(self, qlow, qhigh, qgroup=None, pair_capacity: Optional[int] = None, want_query_ids: bool = True):
+        """(offsets, hit_query, hit_target) for the whole batch -- ``bcu_join``.
 
-        ``pair_capacity`` defaults to a guess and is grown once on ``BCU_E_CAPACITY``.
+        ``pair_capacity`` defaults to a guess and is grown once on ``BCU_E_CAPACITY``. With
+        ``want_query_ids=False`` the (redundant with ``offsets``) query-id column is not produced or copied
+        and ``hit_query`` is returned as ``None``.
         """
         qlow, qhigh, qgroup = self._queries(qlow, qhigh, qgroup)
         lib = _lib.load()
@@ -125,15 +127,15 @@ class DeviceIndex:
         cap = int(pair_capacity) if pair_capacity is not None else max(4 * qlow.size, 1 << 16)
         total = C.c_uint64()
         for _ in range(2):
-            hq = np.empty(cap, dtype=np.uint32)
+            hq = np.empty(cap, dtype=np.uint32) if want_query_ids else None
             ht = np.empty(cap, dtype=np.uint32)
             rc = lib.bcu_join(self._h, qlow.size, _p(qgroup), _p(qlow), _p(qhigh), offsets.ctypes.data,
-                              cap, hq.ctypes.data, ht.ctypes.data, C.byref(total))
+                              cap, _p(hq), ht.ctypes.data, C.byref(total))
             if rc == _lib.BCU_E_CAPACITY:
                 cap = total.value
                 continue
             check(rc)
-            return offsets, hq[: total.value], ht[: total.value]
+            return offsets, (hq[: total.value] if want_query_ids else None), ht[: total.value]
         raise _lib.BinaryCudaError(_lib.BCU_E_CAPACITY, "pair capacity still too small after growing")
 
     def any(self, qlow, qhigh, qgroup=None) -> np.ndarray:
@@ -206,7 +208,7 @@ class IntervalTree:
 
     def find_overlaps_batch(self, qlow, qhigh, qgroup=None):
         """CSR ``(offsets u64[n_q+1], target_ids u32[total])``; ids are insertion ordinals."""
-        offsets, _, target = self._ensure().join(qlow, qhigh, qgroup)
+        offsets, _, target = self._ensure().join(qlow, qhigh, qgroup, want_query_ids=False)
         return offsets, target
 
     def find_overlaps(self, low: int, high: int, group: int = 0):

@@ -286,9 +286,8 @@ namespace algorithm::tree {
       // first try with room for 4 hits per query, grow once to the exact size if that is not enough
       std::uint64_t capacity = 4 * static_cast<std::uint64_t>(n) + 1024;
       for (int attempt = 0; attempt < 2; ++attempt) {
-        std::vector<std::uint32_t> hit_query(capacity);
         res.target_ids.resize(capacity);
-        const int rc = bcu_join(ix, n, nullptr, ql, qh, res.offsets.data(), capacity, hit_query.data(),
+        const int rc = bcu_join(ix, n, nullptr, ql, qh, res.offsets.data(), capacity, /*hit_query=*/nullptr,
                                 res.target_ids.data(), &total);
         if (rc == BCU_E_CAPACITY) {
           capacity = total;

@@ -95,8 +95,9 @@ int bcu_query_scatter(const bcu_index* index, uint64_t n_q, const uint32_t* qgro
 /* One call for the whole join (what the sv2nl loop switches to): the batch is cut into chunks that are
  * pipelined over copy-in / compute / copy-out streams. pair_capacity = entries available in
  * hit_query/hit_target; if the join produces more, returns BCU_E_CAPACITY with *total = required entries
- * (offsets are complete and valid in that case, pairs are not). Staging buffers are cached per host
- * thread; bcu_trim() releases them. */
+ * (offsets are complete and valid in that case, pairs are not). hit_query may be NULL: the column is
+ * redundant with the offsets and skipping it saves a fifth of the device-to-host traffic on sparse joins.
+ * Staging buffers are cached per host thread; bcu_trim() releases them. */
 int bcu_join(const bcu_index* index, uint64_t n_q, const uint32_t* qgroup, const uint32_t* qlow,
              const uint32_t* qhigh, uint64_t* offsets, uint64_t pair_capacity, uint32_t* hit_query,
              uint32_t* hit_target, uint64_t* total);
@@ -116,7 +117,8 @@ int bcu_query_scatter_dev(const bcu_index* index, uint64_t n_q, const uint32_t* 
                           void* stream);
 /* Count + prefix sum + scatter (probe and emit kernels back to back). d_total: u64[1] on device,
  * receives the number of pairs the join has (also when it exceeds pair_capacity, in which case pairs
- * beyond the capacity are not written). query_id_base is added to every emitted query id (sharding). */
+ * beyond the capacity are not written). query_id_base is added to every emitted query id (sharding).
+ * d_hit_query may be NULL (column not produced). */
 int bcu_join_dev(const bcu_index* index, uint64_t n_q, const uint32_t* d_qgroup,
                  const uint32_t* d_qlow, const uint32_t* d_qhigh, uint64_t* d_offsets,
                  uint64_t pair_capacity, uint32_t* d_hit_query, uint32_t* d_hit_target,

@@ -32,6 +32,8 @@ def _check_all_entry_points(c, port):
     off2, hq2, ht2 = ix.join(c["ql"], c["qh"], c["qg"])
     assert np.array_equal(off2, want_off) and np.array_equal(hq2, want_q)
     assert np.array_equal(canonical(off2, ht2)[1], want_tid)
+    off3, hq3, ht3 = ix.join(c["ql"], c["qh"], c["qg"], want_query_ids=False)   # hit_query = NULL
+    assert hq3 is None and np.array_equal(off3, want_off) and np.array_equal(canonical(off3, ht3)[1], want_tid)
     # any-overlap bit (shape-independent part of find_overlap)
     assert np.array_equal(ix.any(c["ql"], c["qh"], c["qg"]), counts > 0)
     ix.close()
