@@ -3,7 +3,8 @@
 Reference being restructured (``/root/reference/standalone/sv2nl``): ``Mapper::map_impl``
 (``include/mapper.hpp:194-236``) builds one tree per chromosome and calls ``find_overlaps`` once per NL
 record; ``TraMapper`` (``source/mapper.cpp:86-170``) shares one tree over all BND records. Here each of the
-three mappers issues ONE batched join for all chromosomes (chromosome = ``group``; Tra = a single group),
+three mappers issues ONE batched join for all chromosomes (chromosome = ``group``; Tra joins on the
+selective breakpoint-proximity condition instead of the raw interval, see below),
 then applies the reference's post-filters (``check_condition``, ``mapper.cpp:50-79,144-156``) vectorised
 on the host over the returned ``(query, target)`` pairs, the duplicate-key rule of ``SV2NL_USE_CACHE``
 (``mapper.hpp:212-234``) and the writer's formatting (``writer.cpp:21-27``).
@@ -106,24 +107,41 @@ def map_sv2nl(nl: VcfTable, sv: VcfTable, diff: int = 1_000_000, use_strand: boo
                                  _fmt(t_chrom[t], t_pos[t], t_end[t], sv.svtype[k]))
         out[name] = lines
 
-    # TraMapper: one tree over ALL BND records, NOT validated; chromosome is not part of the join
+    # TraMapper. The reference joins on the raw [pos, POS2] intervals of ALL BND records (one tree, not
+    # validated, chromosome not part of the key) and then keeps the pairs with equal ordered chromosome
+    # pairs and both breakpoints within `diff` (mapper.cpp:144-156). The raw interval of a translocation
+    # spans two chromosomes' coordinates, so that join returns a large fraction of all BND records per query.
+    # Same result, far fewer pairs: join on the SELECTIVE condition -- group = ordered chromosome pair,
+    # target = the point p1, query = [p1 - diff, p1 + diff] -- and apply the remaining conditions (second
+    # breakpoint within diff, and the reference's raw-interval overlap, which can still reject a pair) on
+    # the host.
     tsel = np.flatnonzero(sv.svtype == "BND")
     qsel = np.flatnonzero((nl.svtype == "TRA") & main)
     lines = []
     if tsel.size and qsel.size:
         q_chrom, q_pos, q_end, q_chr2 = _validated(nl, qsel, swap_chroms=True)
-        ix = DeviceIndex.build(sv.pos[tsel], sv.svend[tsel], None, device=device)
-        off, hq, ht = ix.join(q_pos, q_end, None)
-        ix.close()
 
         def ordered(chrom, pos, chr2, end):  # get_2chroms_with_pos (helper.hpp:76-82)
-            sw = chrom > chr2
+            sw = (chrom > chr2).astype(bool)
             return (np.where(sw, chr2, chrom), np.where(sw, end, pos), np.where(sw, chrom, chr2),
                     np.where(sw, pos, end))
-        n1, np1, n2, np2 = ordered(q_chrom[hq], q_pos[hq], q_chr2[hq], q_end[hq])
-        s1, sp1, s2, sp2 = ordered(sv.chrom[tsel][ht], sv.pos[tsel][ht], sv.chr2[tsel][ht], sv.svend[tsel][ht])
-        ok = (n1 == s1) & (n2 == s2) & (_absdiff(np1, sp1) <= diff) & (_absdiff(np2, sp2) <= diff)
-        hq, ht = hq[ok.astype(bool)], ht[ok.astype(bool)]
+        n1, np1, n2, np2 = ordered(q_chrom, q_pos, q_chr2, q_end)
+        s1, sp1, s2, sp2 = ordered(sv.chrom[tsel], sv.pos[tsel], sv.chr2[tsel], sv.svend[tsel])
+        pair_ids: Dict[tuple, int] = {}
+        pid = lambda a, b: np.array([pair_ids.setdefault((x, y), len(pair_ids)) for x, y in zip(a, b)],
+                                    dtype=np.uint32)
+        t_group, q_group = pid(s1, s2), pid(n1, n2)
+        p1 = np1.astype(np.int64)
+        q_lo = np.clip(p1 - diff, 0, 0xFFFFFFFF).astype(np.uint32)
+        q_hi = np.clip(p1 + diff, 0, 0xFFFFFFFF).astype(np.uint32)
+        sp1u = sp1.astype(np.uint32)
+        ix = DeviceIndex.build(sp1u, sp1u, t_group, device=device)
+        off, hq, ht = ix.join(q_lo, q_hi, q_group)
+        ix.close()
+        t_pos, t_end = sv.pos[tsel], sv.svend[tsel]
+        ok = (_absdiff(np1[hq], sp1[ht]) <= diff) & (_absdiff(np2[hq], sp2[ht]) <= diff)
+        ok &= (q_pos[hq] <= t_end[ht]) & (t_pos[ht] <= q_end[hq])   # the reference's raw overlap, as written
+        hq, ht = hq[ok], ht[ok]
         kept = np.bincount(hq, minlength=qsel.size) > 0
         keys = []
         for i in qsel:  # format_map_key of the ORIGINAL record
