@@ -275,3 +275,35 @@ def test_group_lookup_modes(port_oracle, label, groups):
     ql = rng.integers(0, 500_000, n_q).astype(np.uint32)
     qh = (ql + rng.integers(0, 300, n_q)).astype(np.uint32)
     _check_all_entry_points(dict(tl=tl, th=th, tg=tg, ql=ql, qh=qh, qg=qg), port_oracle)
+
+
+def test_concurrent_host_threads_share_one_index(port_oracle):
+    """The ABI promises that an immutable index may be queried from several host threads at once (the
+    reference shares one tree across its pool threads, sv2nl mapper.cpp:136-140). ctypes drops the GIL
+    during the calls, so these really overlap; each thread has its own staging context and streams."""
+    import threading
+    c = random_case(66, n_t=50000, n_q=40000, n_groups=4, long_frac=0.001)
+    ix = DeviceIndex.build(c["tl"], c["th"], c["tg"])
+    f = port_oracle.build(c["tl"], c["th"], c["tg"])
+    results, errors = {}, []
+
+    def worker(k):
+        try:
+            lo, hi = k * 10000, (k + 1) * 10000
+            for rep in range(3):
+                off, hq, ht = ix.join(c["ql"][lo:hi], c["qh"][lo:hi], c["qg"][lo:hi])
+                cnt = ix.count(c["ql"][lo:hi], c["qh"][lo:hi], c["qg"][lo:hi])
+                assert np.array_equal(off, cnt)
+            results[k] = (off, ht)
+        except Exception as e:  # noqa: BLE001
+            errors.append((k, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    for k in range(4):
+        lo, hi = k * 10000, (k + 1) * 10000
+        want_off, want_tid = f.query_sorted_pairs(c["ql"][lo:hi], c["qh"][lo:hi], c["qg"][lo:hi])
+        off, ht = results[k]
+        assert np.array_equal(off, want_off) and np.array_equal(canonical(off, ht)[1], want_tid)
