@@ -1,0 +1,73 @@
+// sv2nl on the B200 join: same command line as the reference tool (standalone/sv2nl/source/main.cpp:83-165)
+//   sv2nl --sv <delly.vcf[.gz]> --non-linear <scannls.vcf[.gz]> [--dis N] [-o out.tsv] [-t N] [-s] [-d] [-h] [-v]
+// writes <output>.dup, <output>.inv, <output>.tra (main.cpp:30-32), each starting with the header line.
+// -t is accepted and ignored (the GPU join replaces the per-chromosome thread pool); -m (merge) is not
+// implemented.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <string>
+
+#include "mapper.hpp"
+
+static void usage() {
+  std::puts(
+      "Map structural Variation to Non-Linear Transcription (B200 join)\n"
+      "Usage: sv2nl [OPTION...]\n"
+      "      --sv arg          The file path of segment information from delly\n"
+      "      --non-linear arg  The file path of non-linear information from scannls\n"
+      "      --dis arg         The distance threshold for trans mapper (default: 1000000)\n"
+      "  -o, --output arg      The file path of output (default: output.tsv)\n"
+      "  -t, --thread arg      accepted for compatibility, ignored\n"
+      "  -s, --short           If running in short read and do not use strand\n"
+      "      --device arg      CUDA device (default: 0)\n"
+      "  -d, --debug           Print debug info\n"
+      "  -h, --help            Print help\n"
+      "  -v, --version         Print the current version number");
+}
+
+int main(int argc, char** argv) {
+  std::string sv_path, nl_path, output = "output.tsv";
+  sv2nl::Options opt;
+  bool debug = false;
+  for (int i = 1; i < argc; ++i) {
+    std::string a = argv[i];
+    auto value = [&](const char* name) -> std::string {
+      if (i + 1 >= argc) { std::fprintf(stderr, "option %s needs a value\n", name); std::exit(2); }
+      return argv[++i];
+    };
+    if (a == "-h" || a == "--help") { usage(); return 0; }
+    if (a == "-v" || a == "--version") { std::printf("sv2nl (binary_b200) %s\n", bcu_version()); return 0; }
+    if (a == "--sv") sv_path = value("--sv");
+    else if (a == "--non-linear") nl_path = value("--non-linear");
+    else if (a == "--dis") opt.diff = (std::uint32_t)std::stoul(value("--dis"));
+    else if (a == "-o" || a == "--output") output = value("-o");
+    else if (a == "-t" || a == "--thread") (void)value("-t");
+    else if (a == "-s" || a == "--short") opt.use_strand = false;
+    else if (a == "--device") opt.device = std::stoi(value("--device"));
+    else if (a == "-d" || a == "--debug") debug = true;
+    else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); usage(); return 2; }
+  }
+  if (sv_path.empty() || nl_path.empty()) { usage(); return 2; }
+  try {
+    auto nl = sv2nl::read_vcf(nl_path, "nls");
+    auto sv = sv2nl::read_vcf(sv_path, "delly");
+    if (debug) std::fprintf(stderr, "nl records %zu, sv records %zu, diff %u\n", nl.size(), sv.size(), opt.diff);
+    auto res = sv2nl::map_sv2nl(nl, sv, opt);
+    auto write = [&](const char* ext, const std::vector<std::string>& lines) {
+      std::ofstream ofs(output + ext);
+      ofs << sv2nl::HEADER << '\n';
+      for (auto const& l : lines) ofs << l << '\n';
+    };
+    write(".dup", res.dup);
+    write(".inv", res.inv);
+    write(".tra", res.tra);
+    if (debug) std::fprintf(stderr, "dup %zu inv %zu tra %zu lines\n", res.dup.size(), res.inv.size(), res.tra.size());
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "sv2nl: %s\n", e.what());  // the reference's pool swallows this silently (thread_pool.hpp:156-159)
+    return 1;
+  }
+  return 0;
+}

@@ -1,0 +1,217 @@
+// sv2nl's three mappers on top of the batched GPU join (libbinary_cuda, include/binary_cuda.h).
+//
+// Reference being restructured (standalone/sv2nl in the reference checkout):
+//   Mapper::map_delegate / map_impl / build_tree   include/mapper.hpp:147-162, 194-246  (one tree per
+//                                                  chromosome, one find_overlaps per NL record)
+//   Dup/Inv/TraMapper::check_condition             source/mapper.cpp:50-79, 144-156
+//   TraMapper: one tree over all BND records       source/mapper.cpp:86-170
+//   validate_record, is_contained, distance_less,
+//   get_2chroms_with_pos, format_map_key           include/helper.hpp:16-91
+//   SV2NL_USE_CACHE duplicate-key rule             include/mapper.hpp:212-234, options.hpp:8
+// Here every mapper issues ONE batched join over all chromosomes (chromosome = group), then runs the
+// reference's post-filters over the returned (query, target) pairs in query order. Both VCFs are parsed
+// once. Output lines equal the reference's as a multiset (its line order is thread-dependent).
+#pragma once
+
+#include <binary_cuda.h>
+
+#include <algorithm>
+#include <array>
+#include <cstdint>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <unordered_set>
+#include <utility>
+#include <vector>
+
+#include "vcf_text.hpp"
+
+namespace sv2nl {
+
+constexpr const char* HEADER = "chrom\tpos\tend\tsvtype\tchrom\tpos\tend\tsvtype";  // mapper.hpp:30
+
+struct Rec {  // the fields of Sv2nlVcfRecord the mapping reads
+  std::string chrom, chr2, svtype;
+  std::uint32_t pos{}, svend{};
+  bool strand1{true}, strand2{true};
+};
+
+inline Rec record_at(const VcfTable& t, std::size_t i) {
+  return Rec{t.chrom[i], t.chr2[i], t.svtype[i], t.pos[i], t.svend[i], t.strand1[i] != 0, t.strand2[i] != 0};
+}
+
+inline Rec validate_record(Rec r) {  // helper.hpp:52-63
+  if (r.pos > r.svend) {
+    std::swap(r.pos, r.svend);
+    if (r.svtype == "BND" || r.svtype == "TRA") std::swap(r.chrom, r.chr2);
+  }
+  return r;
+}
+inline bool is_contained(const Rec& target, const Rec& source) {  // helper.hpp:16-25
+  return target.pos <= source.pos && target.svend >= source.svend;
+}
+inline std::uint32_t absdiff(std::uint32_t a, std::uint32_t b) { return a >= b ? a - b : b - a; }
+inline bool distance_less(const Rec& a, const Rec& b, std::uint32_t thr) {  // helper.hpp:32-41
+  return absdiff(a.pos, b.pos) <= thr && absdiff(a.svend, b.svend) <= thr;
+}
+struct Breakpoints { std::string c1, c2; std::uint32_t p1, p2; };
+inline Breakpoints ordered_breakpoints(const Rec& r) {  // get_2chroms_with_pos, helper.hpp:76-82
+  return r.chrom > r.chr2 ? Breakpoints{r.chr2, r.chrom, r.svend, r.pos} : Breakpoints{r.chrom, r.chr2, r.pos, r.svend};
+}
+inline std::string format_map_key(const Rec& r) {  // helper.hpp:84-91
+  if (r.svtype == "TRA" || r.svtype == "BND") {
+    auto b = ordered_breakpoints(r);
+    return b.c1 + "-" + b.c2 + "-" + std::to_string(b.p1) + "-" + std::to_string(b.p2);
+  }
+  return r.chrom + "-" + std::to_string(r.pos) + "-" + std::to_string(r.svend);
+}
+inline std::string format_keys(const Rec& r) {  // writer.cpp:21-27 (note pos + 1)
+  std::string c = (r.svtype == "TRA" || r.svtype == "BND") ? r.chrom + "," + r.chr2 : r.chrom;
+  return c + "\t" + std::to_string(r.pos + 1) + "\t" + std::to_string(r.svend) + "\t" + r.svtype;
+}
+
+struct JoinResult {
+  std::vector<std::uint64_t> offsets;
+  std::vector<std::uint32_t> targets;
+};
+
+// one batched join through the C ABI; throws binary::VcfReaderError with the library's message on failure
+inline JoinResult gpu_join(int device, const std::vector<std::uint32_t>& tg, const std::vector<std::uint32_t>& tl,
+                           const std::vector<std::uint32_t>& th, const std::vector<std::uint32_t>& qg,
+                           const std::vector<std::uint32_t>& ql, const std::vector<std::uint32_t>& qh) {
+  JoinResult r;
+  r.offsets.assign(ql.size() + 1, 0);
+  if (tl.empty() || ql.empty()) return r;
+  auto check = [](int rc) {
+    if (rc != BCU_OK) throw binary::VcfReaderError(std::string("libbinary_cuda: ") + bcu_last_error());
+  };
+  bcu_index* ix = nullptr;
+  check(bcu_index_build(device, tl.size(), tg.data(), tl.data(), th.data(), &ix));
+  std::uint64_t total = 0, cap = 4 * ql.size() + 1024;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    r.targets.resize(cap);
+    int rc = bcu_join(ix, ql.size(), qg.data(), ql.data(), qh.data(), r.offsets.data(), cap, nullptr,
+                      r.targets.data(), &total);
+    if (rc == BCU_E_CAPACITY) { cap = total; continue; }
+    if (rc != BCU_OK) { bcu_index_free(ix); check(rc); }
+    break;
+  }
+  bcu_index_free(ix);
+  r.targets.resize(total);
+  return r;
+}
+
+struct Options {
+  std::uint32_t diff = 1000000;  // --dis default, main.cpp:91
+  bool use_strand = true;
+  int device = 0;
+};
+
+struct Sv2nlOutput { std::vector<std::string> dup, inv, tra; };
+
+namespace detail {
+struct Ids {
+  std::unordered_map<std::string, std::uint32_t> map;
+  std::uint32_t operator()(const std::string& s) { return map.try_emplace(s, (std::uint32_t)map.size()).first->second; }
+};
+
+// the common tail of the three map_impl loops: post-filter, duplicate-key rule, formatting
+template <class Check>
+std::vector<std::string> emit_lines(const std::vector<Rec>& nl_orig, const std::vector<Rec>& nl_valid,
+                                    const std::vector<Rec>& sv_recs, const JoinResult& jr, Check&& check) {
+  std::vector<std::string> lines;
+  std::unordered_set<std::string> written;  // SV2NL_USE_CACHE: keys of NL records already written
+  for (std::size_t q = 0; q < nl_orig.size(); ++q) {
+    std::string key = format_map_key(nl_orig[q]);
+    if (written.count(key)) continue;
+    std::vector<std::uint32_t> kept;
+    for (std::uint64_t k = jr.offsets[q]; k < jr.offsets[q + 1]; ++k)
+      if (check(nl_valid[q], sv_recs[jr.targets[k]])) kept.push_back(jr.targets[k]);
+    if (kept.empty()) continue;
+    written.insert(std::move(key));
+    const std::string left = format_keys(nl_orig[q]);
+    for (auto t : kept) lines.push_back(left + "\t" + format_keys(sv_recs[t]));
+  }
+  return lines;
+}
+}  // namespace detail
+
+inline Sv2nlOutput map_sv2nl(const VcfTable& nl, const VcfTable& sv, const Options& opt) {
+  Sv2nlOutput out;
+  std::unordered_set<std::string> main_contigs;  // header contigs without '_' (mapper.hpp:239-244)
+  for (auto const& c : nl.contigs)
+    if (c.find('_') == std::string::npos) main_contigs.insert(c);
+  detail::Ids ids;
+
+  // ---- DupMapper / InvMapper: overlap join per chromosome ------------------------------------------
+  struct Kind { const char* nl_type; const char* sv_type; bool inv; };
+  for (Kind kind : {Kind{"TDUP", "DUP", false}, Kind{"INV", "INV", true}}) {
+    std::vector<Rec> sv_recs, nl_orig, nl_valid;
+    std::vector<std::uint32_t> tg, tl, th, qg, ql, qh;
+    for (std::size_t i = 0; i < sv.size(); ++i)
+      if (sv.svtype[i] == kind.sv_type) {
+        sv_recs.push_back(validate_record(record_at(sv, i)));  // build_tree validates (mapper.hpp:151)
+        tg.push_back(ids(sv_recs.back().chrom)); tl.push_back(sv_recs.back().pos); th.push_back(sv_recs.back().svend);
+      }
+    for (std::size_t i = 0; i < nl.size(); ++i)
+      if (nl.svtype[i] == kind.nl_type && main_contigs.count(nl.chrom[i])) {
+        nl_orig.push_back(record_at(nl, i));
+        nl_valid.push_back(validate_record(nl_orig.back()));
+        qg.push_back(ids(nl_valid.back().chrom)); ql.push_back(nl_valid.back().pos); qh.push_back(nl_valid.back().svend);
+      }
+    JoinResult jr = gpu_join(opt.device, tg, tl, th, qg, ql, qh);
+    auto check_dup = [&](const Rec& n, const Rec& s) {  // mapper.cpp:50-55
+      return is_contained(s, n) && distance_less(n, s, opt.diff);
+    };
+    auto check_inv = [&](const Rec& n, const Rec& s) {  // mapper.cpp:57-79
+      if (is_contained(s, n) || is_contained(n, s) || !distance_less(n, s, opt.diff)) return false;
+      if (!opt.use_strand) return true;
+      if (n.pos <= s.pos) return n.strand1 && !n.strand2;
+      return !n.strand1 && n.strand2;
+    };
+    if (kind.inv) out.inv = detail::emit_lines(nl_orig, nl_valid, sv_recs, jr, check_inv);
+    else out.dup = detail::emit_lines(nl_orig, nl_valid, sv_recs, jr, check_dup);
+  }
+
+  // ---- TraMapper ----------------------------------------------------------------------------------
+  // The reference joins on the raw [pos, POS2] intervals of ALL BND records (not validated, chromosome
+  // not part of the key) and filters afterwards (mapper.cpp:144-156). Same result with far fewer pairs:
+  // join on the selective condition (group = ordered chromosome pair, target = point p1, query =
+  // [p1 - diff, p1 + diff]) and apply the rest -- second breakpoint, and the reference's raw overlap,
+  // which can still reject a pair -- on the host.
+  {
+    std::vector<Rec> sv_recs, nl_orig, nl_valid;
+    std::vector<std::uint32_t> tg, tl, th, qg, ql, qh;
+    std::map<std::pair<std::string, std::string>, std::uint32_t> pair_ids;
+    auto pair_id = [&](const Breakpoints& b) {
+      return pair_ids.try_emplace({b.c1, b.c2}, (std::uint32_t)pair_ids.size()).first->second;
+    };
+    for (std::size_t i = 0; i < sv.size(); ++i)
+      if (sv.svtype[i] == "BND") {
+        sv_recs.push_back(record_at(sv, i));  // NOT validated (mapper.cpp:158-170)
+        auto b = ordered_breakpoints(sv_recs.back());
+        tg.push_back(pair_id(b)); tl.push_back(b.p1); th.push_back(b.p1);
+      }
+    for (std::size_t i = 0; i < nl.size(); ++i)
+      if (nl.svtype[i] == "TRA" && main_contigs.count(nl.chrom[i])) {
+        nl_orig.push_back(record_at(nl, i));
+        nl_valid.push_back(validate_record(nl_orig.back()));
+        auto b = ordered_breakpoints(nl_valid.back());
+        qg.push_back(pair_id(b));
+        ql.push_back(b.p1 > opt.diff ? b.p1 - opt.diff : 0u);
+        qh.push_back(b.p1 <= 0xffffffffu - opt.diff ? b.p1 + opt.diff : 0xffffffffu);
+      }
+    JoinResult jr = gpu_join(opt.device, tg, tl, th, qg, ql, qh);
+    auto check_tra = [&](const Rec& n, const Rec& s) {
+      auto a = ordered_breakpoints(n), b = ordered_breakpoints(s);
+      if (!(a.c1 == b.c1 && a.c2 == b.c2)) return false;
+      if (!(absdiff(a.p1, b.p1) <= opt.diff && absdiff(a.p2, b.p2) <= opt.diff)) return false;
+      return n.pos <= s.svend && s.pos <= n.svend;  // the reference's find_overlaps on the raw intervals
+    };
+    out.tra = detail::emit_lines(nl_orig, nl_valid, sv_recs, jr, check_tra);
+  }
+  return out;
+}
+
+}  // namespace sv2nl

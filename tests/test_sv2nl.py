@@ -76,3 +76,47 @@ def test_gpu_mapping_equals_oracle(port_oracle, tmp_path, case):
     counts = run(nl_path, sv_path, str(tmp_path / "out.tsv"), diff=diff, use_strand=strand)
     assert counts == {k: len(v) for k, v in want.items()}
     assert open(tmp_path / "out.tsv.dup").readline().rstrip("\n") == HEADER == sv2nl_oracle.HEADER
+
+
+# ---- the C++ tool (standalone/sv2nl): same CLI as the reference's sv2nl ---------------------------------
+import subprocess
+
+TOOL_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "standalone", "sv2nl")
+
+
+@pytest.fixture(scope="module")
+def sv2nl_tool():
+    r = subprocess.run(["make", "-C", TOOL_DIR, "sv2nl"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return os.path.join(TOOL_DIR, "sv2nl")
+
+
+def test_cpp_tool_builds_and_prints_help(sv2nl_tool):
+    # the reference CI's only sv2nl check is `sv2nl -h` (.github/workflows/linux.yml:109-111)
+    r = subprocess.run([sv2nl_tool, "-h"], capture_output=True, text=True)
+    assert r.returncode == 0 and "--non-linear" in r.stdout and "--sv" in r.stdout
+    assert subprocess.run([sv2nl_tool], capture_output=True).returncode == 2
+    bad = subprocess.run([sv2nl_tool, "--sv", "/nonexistent.vcf", "--non-linear", NL], capture_output=True, text=True)
+    assert bad.returncode == 1 and "cannot open" in bad.stderr      # fails loudly, unlike the reference's pool
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["fixture", "synthetic", "synthetic-nostrand"])
+def test_cpp_tool_output_equals_oracle(sv2nl_tool, port_oracle, tmp_path, case):
+    if case == "fixture":
+        nl_path, sv_path, diff, strand = NL, SV, 1_000_000, True
+    else:
+        nl_path, sv_path = write_synth_vcfs(str(tmp_path), seed=7, n_sv=5000, n_nl=4000)
+        diff, strand = 3500, case == "synthetic"
+    want = sv2nl_oracle.sv2nl(port_oracle, read_vcf(nl_path, "nls"), read_vcf(sv_path, "delly"), diff=diff,
+                              use_strand=strand)
+    out = str(tmp_path / "out.tsv")
+    cmd = [sv2nl_tool, "--sv", sv_path, "--non-linear", nl_path, "--dis", str(diff), "-o", out, "-t", "4"]
+    if not strand:
+        cmd.append("-s")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    for ext in ("dup", "inv", "tra"):
+        lines = open(f"{out}.{ext}").read().splitlines()
+        assert lines[0] == sv2nl_oracle.HEADER
+        assert sorted(lines[1:]) == sorted(want[ext]), ext
