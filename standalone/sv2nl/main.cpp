@@ -3,6 +3,7 @@
 // writes <output>.dup, <output>.inv, <output>.tra (main.cpp:30-32), each starting with the header line.
 // -t is accepted and ignored (the GPU join replaces the per-chromosome thread pool); -m (merge) is not
 // implemented.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -52,10 +53,15 @@ int main(int argc, char** argv) {
   }
   if (sv_path.empty() || nl_path.empty()) { usage(); return 2; }
   try {
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto secs = [](auto a, auto b) { return std::chrono::duration<double>(b - a).count(); };
+    auto t0 = now();
     auto nl = sv2nl::read_vcf(nl_path, "nls");
     auto sv = sv2nl::read_vcf(sv_path, "delly");
+    auto t1 = now();
     if (debug) std::fprintf(stderr, "nl records %zu, sv records %zu, diff %u\n", nl.size(), sv.size(), opt.diff);
     auto res = sv2nl::map_sv2nl(nl, sv, opt);
+    auto t2 = now();
     auto write = [&](const char* ext, const std::vector<std::string>& lines) {
       std::ofstream ofs(output + ext);
       ofs << sv2nl::HEADER << '\n';
@@ -64,7 +70,10 @@ int main(int argc, char** argv) {
     write(".dup", res.dup);
     write(".inv", res.inv);
     write(".tra", res.tra);
-    if (debug) std::fprintf(stderr, "dup %zu inv %zu tra %zu lines\n", res.dup.size(), res.inv.size(), res.tra.size());
+    auto t3 = now();
+    if (debug)
+      std::fprintf(stderr, "dup %zu inv %zu tra %zu lines; parse %.3f s, map (join + filters) %.3f s, write %.3f s\n",
+                   res.dup.size(), res.inv.size(), res.tra.size(), secs(t0, t1), secs(t1, t2), secs(t2, t3));
   } catch (const std::exception& e) {
     std::fprintf(stderr, "sv2nl: %s\n", e.what());  // the reference's pool swallows this silently (thread_pool.hpp:156-159)
     return 1;

@@ -31,20 +31,52 @@ namespace sv2nl {
 
 constexpr const char* HEADER = "chrom\tpos\tend\tsvtype\tchrom\tpos\tend\tsvtype";  // mapper.hpp:30
 
+// Records are handled as integers (chromosome ids, type codes); strings are only produced for the lines
+// that are actually written. Chromosome ids are ranks in lexicographic name order, so the reference's
+// string comparison `record.chrom > chr2` (helper.hpp:76-82) is an integer comparison here.
 struct Rec {  // the fields of Sv2nlVcfRecord the mapping reads
-  std::string chrom, chr2, svtype;
+  std::uint32_t chrom{}, chr2{};
   std::uint32_t pos{}, svend{};
+  std::uint8_t type{};  // index into Names::types
+  bool two_chrom{};     // SVTYPE is TRA or BND
   bool strand1{true}, strand2{true};
 };
 
-inline Rec record_at(const VcfTable& t, std::size_t i) {
-  return Rec{t.chrom[i], t.chr2[i], t.svtype[i], t.pos[i], t.svend[i], t.strand1[i] != 0, t.strand2[i] != 0};
+struct Names {  // id <-> string tables shared by both files
+  std::vector<std::string> chroms;  // sorted: id order == lexicographic order
+  std::vector<std::string> types;
+  std::unordered_map<std::string, std::uint32_t> chrom_id, type_id;
+  void build(const VcfTable& a, const VcfTable& b) {
+    for (const VcfTable* t : {&a, &b}) {
+      for (auto const& c : t->contigs) chrom_id.emplace(c, 0);
+      for (auto const& c : t->chrom) chrom_id.emplace(c, 0);
+      for (auto const& c : t->chr2) chrom_id.emplace(c, 0);
+      for (auto const& c : t->svtype) type_id.emplace(c, 0);
+    }
+    for (auto const& kv : chrom_id) chroms.push_back(kv.first);
+    std::sort(chroms.begin(), chroms.end());
+    for (std::uint32_t i = 0; i < chroms.size(); ++i) chrom_id[chroms[i]] = i;
+    for (auto& kv : type_id) { kv.second = (std::uint32_t)types.size(); types.push_back(kv.first); }
+  }
+};
+
+inline Rec record_at(const VcfTable& t, const Names& names, std::size_t i) {
+  Rec r;
+  r.chrom = names.chrom_id.at(t.chrom[i]);
+  r.chr2 = names.chrom_id.at(t.chr2[i]);  // "" for non-TRA/BND records: a valid (smallest) id, never used
+  r.pos = t.pos[i];
+  r.svend = t.svend[i];
+  r.type = (std::uint8_t)names.type_id.at(t.svtype[i]);
+  r.two_chrom = t.svtype[i] == "TRA" || t.svtype[i] == "BND";
+  r.strand1 = t.strand1[i] != 0;
+  r.strand2 = t.strand2[i] != 0;
+  return r;
 }
 
 inline Rec validate_record(Rec r) {  // helper.hpp:52-63
   if (r.pos > r.svend) {
     std::swap(r.pos, r.svend);
-    if (r.svtype == "BND" || r.svtype == "TRA") std::swap(r.chrom, r.chr2);
+    if (r.two_chrom) std::swap(r.chrom, r.chr2);
   }
   return r;
 }
@@ -55,20 +87,33 @@ inline std::uint32_t absdiff(std::uint32_t a, std::uint32_t b) { return a >= b ?
 inline bool distance_less(const Rec& a, const Rec& b, std::uint32_t thr) {  // helper.hpp:32-41
   return absdiff(a.pos, b.pos) <= thr && absdiff(a.svend, b.svend) <= thr;
 }
-struct Breakpoints { std::string c1, c2; std::uint32_t p1, p2; };
+struct Breakpoints { std::uint32_t c1, c2, p1, p2; };
 inline Breakpoints ordered_breakpoints(const Rec& r) {  // get_2chroms_with_pos, helper.hpp:76-82
   return r.chrom > r.chr2 ? Breakpoints{r.chr2, r.chrom, r.svend, r.pos} : Breakpoints{r.chrom, r.chr2, r.pos, r.svend};
 }
-inline std::string format_map_key(const Rec& r) {  // helper.hpp:84-91
-  if (r.svtype == "TRA" || r.svtype == "BND") {
-    auto b = ordered_breakpoints(r);
-    return b.c1 + "-" + b.c2 + "-" + std::to_string(b.p1) + "-" + std::to_string(b.p2);
+// format_map_key (helper.hpp:84-91) as integers: two records get the same key iff the reference's
+// formatted strings are equal
+struct MapKey {
+  std::uint32_t a, b, c, d;
+  bool operator==(const MapKey& o) const { return a == o.a && b == o.b && c == o.c && d == o.d; }
+};
+struct MapKeyHash {
+  std::size_t operator()(const MapKey& k) const {
+    std::uint64_t x = ((std::uint64_t)k.a << 32 | k.b) * 0x9E3779B97F4A7C15ull ^ ((std::uint64_t)k.c << 32 | k.d);
+    x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
+    return (std::size_t)x;
   }
-  return r.chrom + "-" + std::to_string(r.pos) + "-" + std::to_string(r.svend);
+};
+inline MapKey map_key(const Rec& r) {
+  if (r.two_chrom) {
+    auto b = ordered_breakpoints(r);
+    return {b.c1, b.c2, b.p1, b.p2};
+  }
+  return {r.chrom, 0xffffffffu, r.pos, r.svend};
 }
-inline std::string format_keys(const Rec& r) {  // writer.cpp:21-27 (note pos + 1)
-  std::string c = (r.svtype == "TRA" || r.svtype == "BND") ? r.chrom + "," + r.chr2 : r.chrom;
-  return c + "\t" + std::to_string(r.pos + 1) + "\t" + std::to_string(r.svend) + "\t" + r.svtype;
+inline std::string format_keys(const Rec& r, const Names& names) {  // writer.cpp:21-27 (note pos + 1)
+  std::string c = r.two_chrom ? names.chroms[r.chrom] + "," + names.chroms[r.chr2] : names.chroms[r.chrom];
+  return c + "\t" + std::to_string(r.pos + 1) + "\t" + std::to_string(r.svend) + "\t" + names.types[r.type];
 }
 
 struct JoinResult {
@@ -111,27 +156,25 @@ struct Options {
 struct Sv2nlOutput { std::vector<std::string> dup, inv, tra; };
 
 namespace detail {
-struct Ids {
-  std::unordered_map<std::string, std::uint32_t> map;
-  std::uint32_t operator()(const std::string& s) { return map.try_emplace(s, (std::uint32_t)map.size()).first->second; }
-};
-
 // the common tail of the three map_impl loops: post-filter, duplicate-key rule, formatting
 template <class Check>
-std::vector<std::string> emit_lines(const std::vector<Rec>& nl_orig, const std::vector<Rec>& nl_valid,
-                                    const std::vector<Rec>& sv_recs, const JoinResult& jr, Check&& check) {
+std::vector<std::string> emit_lines(const Names& names, const std::vector<Rec>& nl_orig,
+                                    const std::vector<Rec>& nl_valid, const std::vector<Rec>& sv_recs,
+                                    const JoinResult& jr, Check&& check) {
   std::vector<std::string> lines;
-  std::unordered_set<std::string> written;  // SV2NL_USE_CACHE: keys of NL records already written
+  std::unordered_set<MapKey, MapKeyHash> written;  // SV2NL_USE_CACHE: keys of NL records already written
+  std::vector<std::uint32_t> kept;
   for (std::size_t q = 0; q < nl_orig.size(); ++q) {
-    std::string key = format_map_key(nl_orig[q]);
+    if (jr.offsets[q] == jr.offsets[q + 1]) continue;  // no raw overlap: nothing can be kept or cached
+    const MapKey key = map_key(nl_orig[q]);
     if (written.count(key)) continue;
-    std::vector<std::uint32_t> kept;
+    kept.clear();
     for (std::uint64_t k = jr.offsets[q]; k < jr.offsets[q + 1]; ++k)
       if (check(nl_valid[q], sv_recs[jr.targets[k]])) kept.push_back(jr.targets[k]);
     if (kept.empty()) continue;
-    written.insert(std::move(key));
-    const std::string left = format_keys(nl_orig[q]);
-    for (auto t : kept) lines.push_back(left + "\t" + format_keys(sv_recs[t]));
+    written.insert(key);
+    const std::string left = format_keys(nl_orig[q], names);
+    for (auto t : kept) lines.push_back(left + "\t" + format_keys(sv_recs[t], names));
   }
   return lines;
 }
@@ -139,10 +182,11 @@ std::vector<std::string> emit_lines(const std::vector<Rec>& nl_orig, const std::
 
 inline Sv2nlOutput map_sv2nl(const VcfTable& nl, const VcfTable& sv, const Options& opt) {
   Sv2nlOutput out;
-  std::unordered_set<std::string> main_contigs;  // header contigs without '_' (mapper.hpp:239-244)
+  Names names;
+  names.build(nl, sv);
+  std::vector<std::uint8_t> is_main(names.chroms.size(), 0);  // header contigs without '_' (mapper.hpp:239-244)
   for (auto const& c : nl.contigs)
-    if (c.find('_') == std::string::npos) main_contigs.insert(c);
-  detail::Ids ids;
+    if (c.find('_') == std::string::npos) is_main[names.chrom_id.at(c)] = 1;
 
   // ---- DupMapper / InvMapper: overlap join per chromosome ------------------------------------------
   struct Kind { const char* nl_type; const char* sv_type; bool inv; };
@@ -151,14 +195,14 @@ inline Sv2nlOutput map_sv2nl(const VcfTable& nl, const VcfTable& sv, const Optio
     std::vector<std::uint32_t> tg, tl, th, qg, ql, qh;
     for (std::size_t i = 0; i < sv.size(); ++i)
       if (sv.svtype[i] == kind.sv_type) {
-        sv_recs.push_back(validate_record(record_at(sv, i)));  // build_tree validates (mapper.hpp:151)
-        tg.push_back(ids(sv_recs.back().chrom)); tl.push_back(sv_recs.back().pos); th.push_back(sv_recs.back().svend);
+        sv_recs.push_back(validate_record(record_at(sv, names, i)));  // build_tree validates (mapper.hpp:151)
+        tg.push_back(sv_recs.back().chrom); tl.push_back(sv_recs.back().pos); th.push_back(sv_recs.back().svend);
       }
     for (std::size_t i = 0; i < nl.size(); ++i)
-      if (nl.svtype[i] == kind.nl_type && main_contigs.count(nl.chrom[i])) {
-        nl_orig.push_back(record_at(nl, i));
+      if (nl.svtype[i] == kind.nl_type && is_main[names.chrom_id.at(nl.chrom[i])]) {
+        nl_orig.push_back(record_at(nl, names, i));
         nl_valid.push_back(validate_record(nl_orig.back()));
-        qg.push_back(ids(nl_valid.back().chrom)); ql.push_back(nl_valid.back().pos); qh.push_back(nl_valid.back().svend);
+        qg.push_back(nl_valid.back().chrom); ql.push_back(nl_valid.back().pos); qh.push_back(nl_valid.back().svend);
       }
     JoinResult jr = gpu_join(opt.device, tg, tl, th, qg, ql, qh);
     auto check_dup = [&](const Rec& n, const Rec& s) {  // mapper.cpp:50-55
@@ -170,8 +214,8 @@ inline Sv2nlOutput map_sv2nl(const VcfTable& nl, const VcfTable& sv, const Optio
       if (n.pos <= s.pos) return n.strand1 && !n.strand2;
       return !n.strand1 && n.strand2;
     };
-    if (kind.inv) out.inv = detail::emit_lines(nl_orig, nl_valid, sv_recs, jr, check_inv);
-    else out.dup = detail::emit_lines(nl_orig, nl_valid, sv_recs, jr, check_dup);
+    if (kind.inv) out.inv = detail::emit_lines(names, nl_orig, nl_valid, sv_recs, jr, check_inv);
+    else out.dup = detail::emit_lines(names, nl_orig, nl_valid, sv_recs, jr, check_dup);
   }
 
   // ---- TraMapper ----------------------------------------------------------------------------------
@@ -183,19 +227,19 @@ inline Sv2nlOutput map_sv2nl(const VcfTable& nl, const VcfTable& sv, const Optio
   {
     std::vector<Rec> sv_recs, nl_orig, nl_valid;
     std::vector<std::uint32_t> tg, tl, th, qg, ql, qh;
-    std::map<std::pair<std::string, std::string>, std::uint32_t> pair_ids;
+    std::map<std::pair<std::uint32_t, std::uint32_t>, std::uint32_t> pair_ids;
     auto pair_id = [&](const Breakpoints& b) {
       return pair_ids.try_emplace({b.c1, b.c2}, (std::uint32_t)pair_ids.size()).first->second;
     };
     for (std::size_t i = 0; i < sv.size(); ++i)
       if (sv.svtype[i] == "BND") {
-        sv_recs.push_back(record_at(sv, i));  // NOT validated (mapper.cpp:158-170)
+        sv_recs.push_back(record_at(sv, names, i));  // NOT validated (mapper.cpp:158-170)
         auto b = ordered_breakpoints(sv_recs.back());
         tg.push_back(pair_id(b)); tl.push_back(b.p1); th.push_back(b.p1);
       }
     for (std::size_t i = 0; i < nl.size(); ++i)
-      if (nl.svtype[i] == "TRA" && main_contigs.count(nl.chrom[i])) {
-        nl_orig.push_back(record_at(nl, i));
+      if (nl.svtype[i] == "TRA" && is_main[names.chrom_id.at(nl.chrom[i])]) {
+        nl_orig.push_back(record_at(nl, names, i));
         nl_valid.push_back(validate_record(nl_orig.back()));
         auto b = ordered_breakpoints(nl_valid.back());
         qg.push_back(pair_id(b));
@@ -209,7 +253,7 @@ inline Sv2nlOutput map_sv2nl(const VcfTable& nl, const VcfTable& sv, const Optio
       if (!(absdiff(a.p1, b.p1) <= opt.diff && absdiff(a.p2, b.p2) <= opt.diff)) return false;
       return n.pos <= s.svend && s.pos <= n.svend;  // the reference's find_overlaps on the raw intervals
     };
-    out.tra = detail::emit_lines(nl_orig, nl_valid, sv_recs, jr, check_tra);
+    out.tra = detail::emit_lines(names, nl_orig, nl_valid, sv_recs, jr, check_tra);
   }
   return out;
 }
