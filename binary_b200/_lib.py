@@ -25,6 +25,14 @@ class BinaryCudaError(RuntimeError):
         self.status = status
 
 
+class Filter(C.Structure):
+    """``bcu_filter``: kind 1 = sv2nl DUP, 2 = sv2nl INV."""
+    _fields_ = [("kind", C.c_uint32), ("diff", C.c_uint32), ("use_strand", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+FILTER_NONE, FILTER_SV2NL_DUP, FILTER_SV2NL_INV = 0, 1, 2
+
+
 class IndexInfo(C.Structure):
     _fields_ = [("n_targets", C.c_uint64), ("n_groups", C.c_uint32), ("n_components", C.c_uint32),
                 ("bin_shift", C.c_uint32), ("sort_passes", C.c_uint32), ("n_bins", C.c_uint64),
@@ -47,6 +55,8 @@ SIGNATURES = {
     "bcu_query_scatter": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp, vp, vp]),
     "bcu_join": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp, C.c_uint64, vp, vp, u64p]),
     "bcu_trim": (C.c_int, []),
+    "bcu_join_filtered": (C.c_int, [vp, vp, C.c_uint64, vp, vp, vp, vp, vp, C.c_uint64, vp, vp, u64p]),
+    "bcu_join_filtered_dev": (C.c_int, [vp, vp, C.c_uint64, vp, vp, vp, vp, vp, C.c_uint64, vp, vp, vp, C.c_uint32, vp]),
     "bcu_query_any": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp]),
     "bcu_query_count_dev": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp, vp]),
     "bcu_query_scatter_dev": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp, vp, vp, vp]),

@@ -123,6 +123,26 @@ extern "C" int bcu_join_dev(const bcu_index* ix, uint64_t n_q, const uint32_t* d
                      d_hit_target, d_total, nullptr, query_id_base, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int bcu_join_filtered_dev(const bcu_index* ix, const bcu_filter* filter, uint64_t n_q,
+                                     const uint32_t* d_qgroup, const uint32_t* d_qlow, const uint32_t* d_qhigh,
+                                     const uint8_t* d_qstrand, uint64_t* d_offsets, uint64_t pair_capacity,
+                                     uint32_t* d_hit_query, uint32_t* d_hit_target, uint64_t* d_total,
+                                     uint32_t query_id_base, void* stream) {
+  BCU_TRY(check_query_args("bcu_join_filtered_dev", ix, n_q, d_qlow, d_qhigh));
+  if (!filter || !d_offsets || (pair_capacity && !d_hit_target)) {
+    set_error("bcu_join_filtered_dev: NULL filter/output pointer");
+    return BCU_E_INVALID;
+  }
+  if (filter->kind == BCU_FILTER_SV2NL_INV && filter->use_strand && n_q && !d_qstrand) {
+    set_error("bcu_join_filtered_dev: the INV filter with use_strand needs d_qstrand");
+    return BCU_E_INVALID;
+  }
+  DeviceGuard guard(ix->device);
+  return launch_join(ix, kModeFused, n_q, d_qgroup, d_qlow, d_qhigh, d_offsets, pair_capacity, d_hit_query,
+                     d_hit_target, d_total, nullptr, query_id_base, static_cast<cudaStream_t>(stream), nullptr,
+                     filter, d_qstrand);
+}
+
 extern "C" int bcu_query_any_dev(const bcu_index* ix, uint64_t n_q, const uint32_t* d_qgroup,
                                  const uint32_t* d_qlow, const uint32_t* d_qhigh, uint8_t* d_any,
                                  void* stream) {

@@ -21,6 +21,8 @@ struct HostCtx {
   cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
   uint32_t *d_qg = nullptr, *d_ql = nullptr, *d_qh = nullptr;
   uint64_t cap_qg = 0, cap_ql = 0, cap_qh = 0;
+  uint8_t* d_qs = nullptr;  // per-query strand bits of a filtered join
+  uint64_t cap_qs = 0;
   uint64_t* d_off = nullptr;
   uint64_t cap_off = 0;
   uint32_t *d_hq = nullptr, *d_ht = nullptr;
@@ -31,10 +33,12 @@ struct HostCtx {
   std::vector<cudaEvent_t> ev_in, ev_run;
 
   void release() {
-    cudaFree(d_qg); cudaFree(d_ql); cudaFree(d_qh); cudaFree(d_off); cudaFree(d_hq); cudaFree(d_ht);
+    cudaFree(d_qg); cudaFree(d_ql); cudaFree(d_qh); cudaFree(d_qs); cudaFree(d_off); cudaFree(d_hq); cudaFree(d_ht);
     cudaFree(d_totals);
     if (h_totals) cudaFreeHost(h_totals);
     d_qg = d_ql = d_qh = d_hq = d_ht = nullptr;
+    d_qs = nullptr;
+    cap_qs = 0;
     d_off = d_totals = h_totals = nullptr;
     cap_qg = cap_ql = cap_qh = cap_off = cap_hq = cap_ht = cap_chunks = 0;
     for (cudaEvent_t e : ev_in) cudaEventDestroy(e);
@@ -61,7 +65,7 @@ struct HostCtx {
   }
 
   int prepare(int dev, uint64_t n_q, uint64_t pair_capacity, uint64_t n_chunks, bool has_group,
-              bool want_query_ids) {
+              bool want_query_ids, bool has_strand) {
     device = dev;
     if (!s_in) {
       BCU_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
@@ -69,6 +73,7 @@ struct HostCtx {
       BCU_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
     }
     if (has_group) BCU_TRY(grow(&d_qg, &cap_qg, n_q));
+    if (has_strand) BCU_TRY(grow(&d_qs, &cap_qs, n_q));
     BCU_TRY(grow(&d_ql, &cap_ql, n_q));
     BCU_TRY(grow(&d_qh, &cap_qh, n_q));
     BCU_TRY(grow(&d_off, &cap_off, n_q + 1));
@@ -131,9 +136,9 @@ extern "C" int bcu_trim(void) {
   return BCU_OK;
 }
 
-extern "C" int bcu_join(const bcu_index* ix, uint64_t n_q, const uint32_t* qgroup, const uint32_t* qlow,
-                        const uint32_t* qhigh, uint64_t* offsets, uint64_t pair_capacity,
-                        uint32_t* hit_query, uint32_t* hit_target, uint64_t* total) {
+static int join_host(const bcu_index* ix, const bcu_filter* filter, uint64_t n_q, const uint32_t* qgroup,
+                     const uint32_t* qlow, const uint32_t* qhigh, const uint8_t* qstrand, uint64_t* offsets,
+                     uint64_t pair_capacity, uint32_t* hit_query, uint32_t* hit_target, uint64_t* total) {
   if (!ix) { set_error("bcu_join: index is NULL"); return BCU_E_INVALID; }
   if (n_q && (!qlow || !qhigh)) { set_error("bcu_join: qlow/qhigh are NULL"); return BCU_E_INVALID; }
   if (n_q > 0xfffffffeull) { set_error("bcu_join: n_q exceeds 2^32-2"); return BCU_E_LIMIT; }
@@ -162,7 +167,8 @@ extern "C" int bcu_join(const bcu_index* ix, uint64_t n_q, const uint32_t* qgrou
   while (bounds.back() + kHostChunk < n_q) bounds.push_back(bounds.back() + kHostChunk);
   bounds.push_back(n_q);
   const uint64_t n_chunks = bounds.size() - 1;
-  BCU_TRY(c->prepare(ix->device, n_q, pair_capacity, n_chunks, qgroup != nullptr, hit_query != nullptr));
+  BCU_TRY(c->prepare(ix->device, n_q, pair_capacity, n_chunks, qgroup != nullptr, hit_query != nullptr,
+                     qstrand != nullptr));
 
   // 1. queue every chunk's H2D copies and kernels; nothing here blocks the host
   for (uint64_t i = 0; i < n_chunks; ++i) {
@@ -170,11 +176,13 @@ extern "C" int bcu_join(const bcu_index* ix, uint64_t n_q, const uint32_t* qgrou
     if (qgroup) BCU_CUDA(cudaMemcpyAsync(c->d_qg + b, qgroup + b, n * 4, cudaMemcpyHostToDevice, c->s_in));
     BCU_CUDA(cudaMemcpyAsync(c->d_ql + b, qlow + b, n * 4, cudaMemcpyHostToDevice, c->s_in));
     BCU_CUDA(cudaMemcpyAsync(c->d_qh + b, qhigh + b, n * 4, cudaMemcpyHostToDevice, c->s_in));
+    if (qstrand) BCU_CUDA(cudaMemcpyAsync(c->d_qs + b, qstrand + b, n, cudaMemcpyHostToDevice, c->s_in));
     BCU_CUDA(cudaEventRecord(c->ev_in[i], c->s_in));
     BCU_CUDA(cudaStreamWaitEvent(c->s_run, c->ev_in[i], 0));
     BCU_TRY(launch_join(ix, kModeFused, n, qgroup ? c->d_qg + b : nullptr, c->d_ql + b, c->d_qh + b,
                         c->d_off + b, pair_capacity, hit_query ? c->d_hq : nullptr, c->d_ht, c->d_totals + i, nullptr,
-                        (uint32_t)b, c->s_run, i ? c->d_totals + (i - 1) : nullptr));
+                        (uint32_t)b, c->s_run, i ? c->d_totals + (i - 1) : nullptr, filter,
+                        qstrand ? c->d_qs + b : nullptr));
     BCU_CUDA(cudaMemcpyAsync(c->h_totals + i, c->d_totals + i, 8, cudaMemcpyDeviceToHost, c->s_run));
     BCU_CUDA(cudaEventRecord(c->ev_run[i], c->s_run));
   }
@@ -205,4 +213,24 @@ extern "C" int bcu_join(const bcu_index* ix, uint64_t n_q, const uint32_t* qgrou
     return BCU_E_CAPACITY;
   }
   return BCU_OK;
+}
+
+extern "C" int bcu_join(const bcu_index* ix, uint64_t n_q, const uint32_t* qgroup, const uint32_t* qlow,
+                        const uint32_t* qhigh, uint64_t* offsets, uint64_t pair_capacity,
+                        uint32_t* hit_query, uint32_t* hit_target, uint64_t* total) {
+  return join_host(ix, nullptr, n_q, qgroup, qlow, qhigh, nullptr, offsets, pair_capacity, hit_query, hit_target,
+                   total);
+}
+
+extern "C" int bcu_join_filtered(const bcu_index* ix, const bcu_filter* filter, uint64_t n_q,
+                                 const uint32_t* qgroup, const uint32_t* qlow, const uint32_t* qhigh,
+                                 const uint8_t* qstrand, uint64_t* offsets, uint64_t pair_capacity,
+                                 uint32_t* hit_query, uint32_t* hit_target, uint64_t* total) {
+  if (!filter) { set_error("bcu_join_filtered: filter is NULL"); return BCU_E_INVALID; }
+  if (filter->kind == BCU_FILTER_SV2NL_INV && filter->use_strand && n_q && !qstrand) {
+    set_error("bcu_join_filtered: the INV filter with use_strand needs qstrand");
+    return BCU_E_INVALID;
+  }
+  return join_host(ix, filter, n_q, qgroup, qlow, qhigh, qstrand, offsets, pair_capacity, hit_query, hit_target,
+                   total);
 }

@@ -220,10 +220,10 @@ static void keep_pool_warm(int device) {
 static int alloc_rows(bcu_index* ix, uint64_t n, cudaStream_t stream) {
   // Pool allocations (cudaMallocAsync): a rebuild reuses cached device memory instead of paying the
   // driver's map/unmap cost of cudaMalloc/cudaFree (measured: 2 ms vs up to 300 ms per build).
-  BCU_CUDA(cudaMallocAsync((void**)&ix->d_lowhigh, (n + 2) * sizeof(uint2), stream));  // +pad: row PAIRS are read
+  BCU_CUDA(cudaMallocAsync((void**)&ix->d_lowhigh, (n + 4) * sizeof(uint2), stream));  // +pad: 4 rows per load
   BCU_CUDA(cudaMallocAsync((void**)&ix->d_id, (n + 4) * 4, stream));                   // +pad: 4 rows per load
   BCU_CUDA(cudaMallocAsync((void**)&ix->d_high, (n + 4) * 4, stream));
-  BCU_CUDA(cudaMemsetAsync(ix->d_lowhigh + n, 0, 2 * sizeof(uint2), stream));
+  BCU_CUDA(cudaMemsetAsync(ix->d_lowhigh + n, 0, 4 * sizeof(uint2), stream));
   BCU_CUDA(cudaMemsetAsync(ix->d_id + n, 0, 16, stream));
   BCU_CUDA(cudaMemsetAsync(ix->d_high + n, 0, 16, stream));
   return BCU_OK;

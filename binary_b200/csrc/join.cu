@@ -84,6 +84,11 @@ struct JoinArgs {
   uint32_t* st_ub;      // [same] probe state of LONG ranges only: exact end row (untouched otherwise)
   uint64_t* cta_total;  // [gridDim.x] hits per chunk
   const uint64_t* base_in;  // optional: offset of the batch's first pair (chunked host pipeline)
+  // optional pair filter applied ON TOP of the overlap predicate (sv2nl's check_condition, fused)
+  uint32_t filter_kind;     // bcu_filter_kind
+  uint32_t filter_diff;
+  uint32_t filter_use_strand;
+  const uint8_t* __restrict__ qstrand;  // INV: per query, bit0 = strand1 is '+', bit1 = strand2 is '+'
 };
 
 struct GroupTables {
@@ -118,6 +123,29 @@ __device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) {
 
 __device__ __forceinline__ bool overlaps(uint32_t ql, uint32_t qh, uint32_t tl, uint32_t th) {
   return (ql <= th) & (tl <= qh);
+}
+__device__ __forceinline__ uint32_t absdiff(uint32_t a, uint32_t b) { return a >= b ? a - b : b - a; }
+
+// The pair predicate. FILT = false: the reference's is_overlap (interval_tree.hpp:119-121), nothing else.
+// FILT = true: additionally sv2nl's check_condition for the pair (query = validated NL record, target =
+// validated SV record), so that rejected pairs are never counted or written:
+//   DUP (mapper.cpp:50-55):  sv contains nl  &&  both ends within diff
+//   INV (mapper.cpp:57-79):  neither contains the other  &&  both ends within diff  &&  strand rule
+template <bool FILT>
+__device__ __forceinline__ bool accept(uint32_t kind, uint32_t diff, uint32_t use_strand, uint32_t strand,
+                                       uint32_t ql, uint32_t qh, uint32_t tl, uint32_t th) {
+  const bool ov = overlaps(ql, qh, tl, th);
+  if (!FILT) return ov;
+  const bool t_has_q = (tl <= ql) & (th >= qh);                              // is_contained(sv, nl)
+  const bool near = (absdiff(ql, tl) <= diff) & (absdiff(qh, th) <= diff);  // distance_less
+  if (kind == BCU_FILTER_SV2NL_DUP) return ov & t_has_q & near;
+  const bool q_has_t = (ql <= tl) & (qh >= th);                              // is_contained(nl, sv)
+  bool ok = ov & !t_has_q & !q_has_t & near;
+  if (use_strand) {
+    const bool s1 = strand & 1u, s2 = strand & 2u;
+    ok &= (ql <= tl) ? (s1 & !s2) : (!s1 & s2);
+  }
+  return ok;
 }
 
 // group tables -> shared memory, once per CTA (ends with a barrier)
@@ -171,9 +199,11 @@ __device__ __forceinline__ void load_queries(const JoinArgs& a, uint32_t v0, uin
 }
 
 // K3 step 1: candidate row range [lb, lb+len) of one query. `valid` = the query exists.
+template <bool FILT>
 __device__ __forceinline__ void query_bounds(const JoinArgs& a, const GroupTables& tb, bool valid,
                                              uint32_t slot, uint32_t ql, uint32_t qh, uint32_t qg,
-                                             uint32_t& lb, uint32_t& len, uint32_t& inline_mask) {
+                                             uint32_t strand, uint32_t& lb, uint32_t& len,
+                                             uint32_t& inline_mask) {
   const bool in_smem = a.n_groups * a.n_comp <= (uint32_t)kMaxSmemGroups;
   const bool direct = in_smem && a.max_gval < (uint32_t)kDirectGroups;
   lb = 0;
@@ -219,14 +249,17 @@ __device__ __forceinline__ void query_bounds(const JoinArgs& a, const GroupTable
     if (b_hi != b_lo) u = a.dir[bin_base + b_hi].ub;
     lb = e.x;
     len = u > e.x ? u - e.x : 0u;
-    inline_mask = (uint32_t)(len > 0 && overlaps(ql, qh, e.z, e.w));
+    inline_mask = (uint32_t)(len > 0 && accept<FILT>(a.filter_kind, a.filter_diff, a.filter_use_strand, strand,
+                                                     ql, qh, e.z, e.w));
   }
 }
 
 // K3 step 2, short ranges: the 4 queries of a lane advance together (4 independent loads per trip).
+template <bool FILT>
 __device__ __forceinline__ void scan_short(const JoinArgs& a, const uint32_t (&ql)[kQPT],
-                                           const uint32_t (&qh)[kQPT], const uint32_t (&lb)[kQPT],
-                                           const uint32_t (&len)[kQPT], uint32_t (&mask)[kQPT]) {
+                                           const uint32_t (&qh)[kQPT], const uint32_t (&strand)[kQPT],
+                                           const uint32_t (&lb)[kQPT], const uint32_t (&len)[kQPT],
+                                           uint32_t (&mask)[kQPT]) {
   // on entry mask[j] holds the bit of the row that came inline with the directory entry
   uint32_t max_short = 0;
 #pragma unroll
@@ -239,7 +272,8 @@ __device__ __forceinline__ void scan_short(const JoinArgs& a, const uint32_t (&q
     for (int j = 0; j < kQPT; ++j) {
       if (k < len[j] && len[j] <= kScalarMax) {
         const uint2 t = ldg_u2(a.lowhigh + lb[j] + k);
-        mask[j] |= (uint32_t)overlaps(ql[j], qh[j], t.x, t.y) << k;
+        mask[j] |= (uint32_t)accept<FILT>(a.filter_kind, a.filter_diff, a.filter_use_strand, strand[j], ql[j],
+                                          qh[j], t.x, t.y) << k;
       }
     }
   }
@@ -256,15 +290,18 @@ struct LongCtx {  // what the long-range path needs, passed BY VALUE into the ou
                   // that the callers' per-query arrays stay in registers on the (common) short path
   const uint32_t* high;
   const uint32_t* ids;
+  const uint2* lowhigh;  // FILT only: the filter needs t.low as well
   uint32_t* hit_target;
   uint32_t* hit_query;
   uint64_t capacity;
   uint32_t qid_base;
   uint32_t comp_shift;
+  uint32_t filter_kind, filter_diff, filter_use_strand;
 };
 
 struct LongRange {
   uint32_t lb, ub, ql;  // rows [lb, ub), query low
+  uint32_t qh, strand;  // FILT only
   uint32_t cnt;         // EMIT: number of hits (from the probe state)
   uint32_t qid;
   uint64_t base;        // EMIT: output position of the first hit
@@ -288,11 +325,34 @@ __device__ __forceinline__ uint32_t reaches(uint32_t ql, const uint4& h) {
          ((uint32_t)(ql <= h.w) << 3);
 }
 
-template <bool EMIT>
+// FILT: the 4 rows' {low, high} come from two 128-bit loads of `lowhigh` and go through accept<true>
+template <bool FILT>
+__device__ __forceinline__ uint32_t long_mask(const LongCtx& c, const LongRange& R, uint32_t r, uint32_t end,
+                                              bool valid) {
+  if (!FILT) {
+    uint4 h = make_uint4(0, 0, 0, 0);
+    if (valid) h = ldg_u4(reinterpret_cast<const uint4*>(c.high) + (r >> 2));
+    return rows_in_range(r, R.lb, end) & reaches(R.ql, h);
+  } else {
+    uint4 p0 = make_uint4(0, 0, 0, 0), p1 = make_uint4(0, 0, 0, 0);
+    if (valid) {
+      const uint4* pairs = reinterpret_cast<const uint4*>(c.lowhigh) + (r >> 1);
+      p0 = ldg_u4(pairs);
+      p1 = ldg_u4(pairs + 1);
+    }
+    const uint32_t m =
+        (uint32_t)accept<true>(c.filter_kind, c.filter_diff, c.filter_use_strand, R.strand, R.ql, R.qh, p0.x, p0.y) |
+        ((uint32_t)accept<true>(c.filter_kind, c.filter_diff, c.filter_use_strand, R.strand, R.ql, R.qh, p0.z, p0.w) << 1) |
+        ((uint32_t)accept<true>(c.filter_kind, c.filter_diff, c.filter_use_strand, R.strand, R.ql, R.qh, p1.x, p1.y) << 2) |
+        ((uint32_t)accept<true>(c.filter_kind, c.filter_diff, c.filter_use_strand, R.strand, R.ql, R.qh, p1.z, p1.w) << 3);
+    return rows_in_range(r, R.lb, end) & m;
+  }
+}
+
+template <bool EMIT, bool FILT>
 __device__ __forceinline__ void scan_two_long(const LongCtx& c, int lane, const LongRange& A,
                                               const LongRange& B, bool has_b, uint32_t& cnt_a,
                                               uint32_t& cnt_b) {
-  const uint4* high4 = reinterpret_cast<const uint4*>(c.high);
   const uint4* id4 = reinterpret_cast<const uint4*>(c.ids);
   uint32_t ca = 0, cb = 0;  // COUNT: lane-local hit counts; EMIT: hits of the range written so far
   uint32_t ra = (A.lb & ~3u) + 4u * lane, rb = (B.lb & ~3u) + 4u * lane;
@@ -304,16 +364,14 @@ __device__ __forceinline__ void scan_two_long(const LongCtx& c, int lane, const 
   const uint32_t lim_b = c.capacity > B.base ? (uint32_t)min(c.capacity - B.base, (uint64_t)0xffffffffu) : 0u;
   while (((ra - 4u * lane) < end_a) | ((rb - 4u * lane) < end_b)) {  // warp-uniform (lane 0's row)
     const bool va = ra < end_a, vb = rb < end_b;
-    uint4 ha = make_uint4(0, 0, 0, 0), hb = make_uint4(0, 0, 0, 0), ia, ib;
-    if (va) ha = ldg_u4(high4 + (ra >> 2));
-    if (vb) hb = ldg_u4(high4 + (rb >> 2));
+    uint4 ia, ib;
+    const uint32_t ma = long_mask<FILT>(c, A, ra, end_a, va);
+    const uint32_t mb = long_mask<FILT>(c, B, rb, end_b, vb);
     if (EMIT) {
       ia = ib = make_uint4(0, 0, 0, 0);
       if (va) ia = ldg_u4(id4 + (ra >> 2));
       if (vb) ib = ldg_u4(id4 + (rb >> 2));
     }
-    const uint32_t ma = rows_in_range(ra, A.lb, end_a) & reaches(A.ql, ha);
-    const uint32_t mb = rows_in_range(rb, B.lb, end_b) & reaches(B.ql, hb);
     if (!EMIT) {
       ca += __popc(ma);
       cb += __popc(mb);
@@ -375,13 +433,15 @@ __device__ __forceinline__ void scan_two_long(const LongCtx& c, int lane, const 
 // All long ranges of the warp's 128 queries, two at a time. Lane-local inputs per query j (packed in
 // vectors, by value): bit j of `bigbits`, the exact row range [lb.j, ub.j), ql.j; EMIT also needs cnt.j
 // (from the probe) and the absolute output position pos.j. COUNT returns cnt.j of the long ranges.
-template <bool EMIT>
+template <bool EMIT, bool FILT>
 __device__ __noinline__ uint4 long_ranges(LongCtx c, int lane, uint32_t bigbits, uint4 lb4, uint4 ub4,
                                           uint4 ql4, uint4 cnt4, uint64_t pos_0, uint64_t pos_1,
-                                          uint64_t pos_2, uint64_t pos_3, uint32_t vq0) {
+                                          uint64_t pos_2, uint64_t pos_3, uint32_t vq0, uint4 qh4,
+                                          uint32_t strand4) {  // strand4: byte j = strand bits of query j
   const uint32_t lb[kQPT] = {lb4.x, lb4.y, lb4.z, lb4.w};
   const uint32_t ub[kQPT] = {ub4.x, ub4.y, ub4.z, ub4.w};
   const uint32_t ql[kQPT] = {ql4.x, ql4.y, ql4.z, ql4.w};
+  const uint32_t qh[kQPT] = {qh4.x, qh4.y, qh4.z, qh4.w};
   uint32_t cnt[kQPT] = {cnt4.x, cnt4.y, cnt4.z, cnt4.w};
   const uint64_t pos0[kQPT] = {pos_0, pos_1, pos_2, pos_3};
 #pragma unroll
@@ -397,6 +457,12 @@ __device__ __noinline__ uint4 long_ranges(LongCtx c, int lane, uint32_t bigbits,
       A.lb = __shfl_sync(0xffffffffu, lb[j], sa); B.lb = __shfl_sync(0xffffffffu, lb[j], sb);
       A.ub = __shfl_sync(0xffffffffu, ub[j], sa); B.ub = __shfl_sync(0xffffffffu, ub[j], sb);
       A.ql = __shfl_sync(0xffffffffu, ql[j], sa); B.ql = __shfl_sync(0xffffffffu, ql[j], sb);
+      A.qh = B.qh = A.strand = B.strand = 0;
+      if (FILT) {
+        A.qh = __shfl_sync(0xffffffffu, qh[j], sa); B.qh = __shfl_sync(0xffffffffu, qh[j], sb);
+        A.strand = (__shfl_sync(0xffffffffu, strand4, sa) >> (8 * j)) & 0xffu;
+        B.strand = (__shfl_sync(0xffffffffu, strand4, sb) >> (8 * j)) & 0xffu;
+      }
       A.qid = c.qid_base + ((vq0 + (uint32_t)sa * kQPT + j) >> c.comp_shift);  // vq0 = warp's first virtual query
       B.qid = c.qid_base + ((vq0 + (uint32_t)sb * kQPT + j) >> c.comp_shift);
       A.cnt = B.cnt = 0;
@@ -406,7 +472,7 @@ __device__ __noinline__ uint4 long_ranges(LongCtx c, int lane, uint32_t bigbits,
         A.base = shfl_u64(pos0[j], sa);               B.base = shfl_u64(pos0[j], sb);
       }
       uint32_t ca = 0, cb = 0;
-      scan_two_long<EMIT>(c, lane, A, B, has_b, ca, cb);
+      scan_two_long<EMIT, FILT>(c, lane, A, B, has_b, ca, cb);
       if (!EMIT) {
         if (lane == sa) cnt[j] = ca;
         if (has_b && lane == sb) cnt[j] = cb;
@@ -422,9 +488,13 @@ __device__ __forceinline__ LongCtx long_ctx(const JoinArgs& a) {
   c.ids = a.ids;
   c.hit_target = a.hit_target;
   c.hit_query = a.hit_query;
+  c.lowhigh = a.lowhigh;
   c.capacity = a.capacity;
   c.qid_base = a.qid_base;
   c.comp_shift = a.comp_shift;
+  c.filter_kind = a.filter_kind;
+  c.filter_diff = a.filter_diff;
+  c.filter_use_strand = a.filter_use_strand;
   return c;
 }
 __device__ __forceinline__ uint32_t pack_bits(const bool (&b)[kQPT]) {
@@ -492,6 +562,7 @@ __device__ __forceinline__ void emit_short(const JoinArgs& a, StageBuffers& st, 
 
 // ---------------------------------------------------------------------------------------------------
 // K3: probe. No barriers inside the chunk loop.
+template <bool FILT>
 __global__ void __launch_bounds__(kJoinThreads, kProbeMinBlocks) probe_kernel(const JoinArgs a) {
   __shared__ GroupTables tb;
   __shared__ uint64_t s_warp_total[kJoinWarps];
@@ -512,11 +583,15 @@ __global__ void __launch_bounds__(kJoinThreads, kProbeMinBlocks) probe_kernel(co
     for (int j = 0; j < kQPT; ++j) { ql[j] = nql[j]; qh[j] = nqh[j]; qg[j] = nqg[j]; }
     if (w0 + kCtaTile < chunk_end) load_queries(a, q0 + kCtaTile, nql, nqh, nqg);
 
-    uint32_t lb[kQPT], len[kQPT], w[kQPT];
+    uint32_t lb[kQPT], len[kQPT], w[kQPT], strand[kQPT];
 #pragma unroll
-    for (int j = 0; j < kQPT; ++j)
-      query_bounds(a, tb, q0 + j < a.n_vq, (q0 + j) & (a.n_comp - 1u), ql[j], qh[j], qg[j], lb[j], len[j], w[j]);
-    scan_short(a, ql, qh, lb, len, w);
+    for (int j = 0; j < kQPT; ++j) {
+      strand[j] = 0;
+      if (FILT && a.qstrand && q0 + j < a.n_vq) strand[j] = a.qstrand[(q0 + j) >> a.comp_shift];
+      query_bounds<FILT>(a, tb, q0 + j < a.n_vq, (q0 + j) & (a.n_comp - 1u), ql[j], qh[j], qg[j], strand[j], lb[j],
+                         len[j], w[j]);
+    }
+    scan_short<FILT>(a, ql, qh, strand, lb, len, w);
     bool big[kQPT];
     uint32_t ub[kQPT];
     bool lane_big = false;
@@ -531,10 +606,11 @@ __global__ void __launch_bounds__(kJoinThreads, kProbeMinBlocks) probe_kernel(co
 #pragma unroll
       for (int j = 0; j < kQPT; ++j)
         if (big[j]) ub[j] = exact_upper_bound(a, lb[j], len[j], qh[j]);
-      const uint4 c4 = long_ranges<false>(long_ctx(a), lane, pack_bits(big), make_uint4(lb[0], lb[1], lb[2], lb[3]),
-                                          make_uint4(ub[0], ub[1], ub[2], ub[3]),
-                                          make_uint4(ql[0], ql[1], ql[2], ql[3]), make_uint4(0, 0, 0, 0), 0, 0,
-                                          0, 0, 0);
+      const uint4 c4 = long_ranges<false, FILT>(
+          long_ctx(a), lane, pack_bits(big), make_uint4(lb[0], lb[1], lb[2], lb[3]),
+          make_uint4(ub[0], ub[1], ub[2], ub[3]), make_uint4(ql[0], ql[1], ql[2], ql[3]), make_uint4(0, 0, 0, 0), 0,
+          0, 0, 0, 0, make_uint4(qh[0], qh[1], qh[2], qh[3]),
+          strand[0] | (strand[1] << 8) | (strand[2] << 16) | (strand[3] << 24));
       const uint32_t cl[kQPT] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
       for (int j = 0; j < kQPT; ++j)
@@ -558,7 +634,7 @@ __global__ void __launch_bounds__(kJoinThreads, kProbeMinBlocks) probe_kernel(co
 
 // ---------------------------------------------------------------------------------------------------
 // K4: prefix sum + scatter. One barrier per 1024 queries, no waiting on other CTAs.
-template <bool EMIT>
+template <bool EMIT, bool FILT>
 __global__ void __launch_bounds__(kJoinThreads, kEmitMinBlocks) emit_kernel(const JoinArgs a) {
   __shared__ StageBuffers st;
   __shared__ uint64_t s_warp_total[2][kJoinWarps];
@@ -670,9 +746,10 @@ __global__ void __launch_bounds__(kJoinThreads, kEmitMinBlocks) emit_kernel(cons
     if (t0 + (uint64_t)tid * kQPT < chunk_end) w4 = *reinterpret_cast<const uint4*>(a.st_w + q0);
     const uint32_t w[kQPT] = {w4.x, w4.y, w4.z, w4.w};
     if (!__any_sync(0xffffffffu, ((w4.x | w4.y | w4.z | w4.w) & kBigFlag) != 0)) continue;
-    uint32_t ql[kQPT], blb[kQPT], bub[kQPT], cnt[kQPT];
+    uint32_t ql[kQPT], qh[kQPT], blb[kQPT], bub[kQPT], cnt[kQPT];
     uint64_t pos[kQPT];
     bool big[kQPT];
+    uint32_t strand4 = 0;
     uint64_t run = 0;  // hits of the earlier slots of the same query (all slots of a query sit in one lane)
 #pragma unroll
     for (int j = 0; j < kQPT; ++j) {
@@ -681,14 +758,17 @@ __global__ void __launch_bounds__(kJoinThreads, kEmitMinBlocks) emit_kernel(cons
       cnt[j] = big[j] ? (w[j] & ~kBigFlag) : (uint32_t)__popc(w[j]);
       if ((v & (a.n_comp - 1u)) == 0) run = 0;
       ql[j] = big[j] ? a.qlow[v >> a.comp_shift] : 0u;
+      qh[j] = (FILT && big[j]) ? a.qhigh[v >> a.comp_shift] : 0u;
+      if (FILT && big[j] && a.qstrand) strand4 |= (uint32_t)a.qstrand[v >> a.comp_shift] << (8 * j);
       blb[j] = big[j] ? a.st_lb[v] : 0u;
       bub[j] = big[j] ? a.st_ub[v] : 0u;
       pos[j] = big[j] ? a.offsets[v >> a.comp_shift] + run : 0ull;
       run += cnt[j];
     }
-    long_ranges<true>(long_ctx(a), lane, pack_bits(big), make_uint4(blb[0], blb[1], blb[2], blb[3]),
-                      make_uint4(bub[0], bub[1], bub[2], bub[3]), make_uint4(ql[0], ql[1], ql[2], ql[3]),
-                      make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]), pos[0], pos[1], pos[2], pos[3], w0);
+    long_ranges<true, FILT>(long_ctx(a), lane, pack_bits(big), make_uint4(blb[0], blb[1], blb[2], blb[3]),
+                            make_uint4(bub[0], bub[1], bub[2], bub[3]), make_uint4(ql[0], ql[1], ql[2], ql[3]),
+                            make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]), pos[0], pos[1], pos[2], pos[3], w0,
+                            make_uint4(qh[0], qh[1], qh[2], qh[3]), strand4);
   }
 }
 
@@ -707,9 +787,12 @@ __global__ void __launch_bounds__(kJoinThreads, kJoinMinBlocks) direct_kernel(co
     uint32_t ql[kQPT], qh[kQPT], qg[kQPT], lb[kQPT], len[kQPT], mask[kQPT];
     load_queries(a, q0, ql, qh, qg);
 #pragma unroll
+    const uint32_t no_strand[kQPT] = {0, 0, 0, 0};
+#pragma unroll
     for (int j = 0; j < kQPT; ++j)
-      query_bounds(a, tb, q0 + j < a.n_vq, (q0 + j) & (a.n_comp - 1u), ql[j], qh[j], qg[j], lb[j], len[j], mask[j]);
-    scan_short(a, ql, qh, lb, len, mask);
+      query_bounds<false>(a, tb, q0 + j < a.n_vq, (q0 + j) & (a.n_comp - 1u), ql[j], qh[j], qg[j], 0u, lb[j], len[j],
+                          mask[j]);
+    scan_short<false>(a, ql, qh, no_strand, lb, len, mask);
     bool big[kQPT];
     uint32_t ub[kQPT], cnt[kQPT];
     bool lane_big = false;
@@ -722,10 +805,11 @@ __global__ void __launch_bounds__(kJoinThreads, kJoinMinBlocks) direct_kernel(co
     }
     const bool warp_big = __any_sync(0xffffffffu, lane_big);
     if (warp_big) {  // hit counts of the long ranges (the caller's offsets only give per-query totals)
-      const uint4 c4 = long_ranges<false>(long_ctx(a), lane, pack_bits(big), make_uint4(lb[0], lb[1], lb[2], lb[3]),
-                                          make_uint4(ub[0], ub[1], ub[2], ub[3]),
-                                          make_uint4(ql[0], ql[1], ql[2], ql[3]), make_uint4(0, 0, 0, 0), 0, 0,
-                                          0, 0, 0);
+      const uint4 c4 = long_ranges<false, false>(long_ctx(a), lane, pack_bits(big),
+                                                 make_uint4(lb[0], lb[1], lb[2], lb[3]),
+                                                 make_uint4(ub[0], ub[1], ub[2], ub[3]),
+                                                 make_uint4(ql[0], ql[1], ql[2], ql[3]), make_uint4(0, 0, 0, 0), 0, 0,
+                                                 0, 0, 0, make_uint4(0, 0, 0, 0), 0);
       const uint32_t cl[kQPT] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
       for (int j = 0; j < kQPT; ++j)
@@ -755,9 +839,10 @@ __global__ void __launch_bounds__(kJoinThreads, kJoinMinBlocks) direct_kernel(co
     }
     emit_short<true>(a, st, warp, lane, mask, lb, off, 0, w0);
     if (warp_big)
-      long_ranges<true>(long_ctx(a), lane, pack_bits(big), make_uint4(lb[0], lb[1], lb[2], lb[3]),
-                        make_uint4(ub[0], ub[1], ub[2], ub[3]), make_uint4(ql[0], ql[1], ql[2], ql[3]),
-                        make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]), off[0], off[1], off[2], off[3], w0);
+      long_ranges<true, false>(long_ctx(a), lane, pack_bits(big), make_uint4(lb[0], lb[1], lb[2], lb[3]),
+                               make_uint4(ub[0], ub[1], ub[2], ub[3]), make_uint4(ql[0], ql[1], ql[2], ql[3]),
+                               make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]), off[0], off[1], off[2], off[3], w0,
+                               make_uint4(0, 0, 0, 0), 0);
   }
 }
 
@@ -782,7 +867,7 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
                 const uint32_t* d_qlow, const uint32_t* d_qhigh, uint64_t* d_offsets,
                 uint64_t pair_capacity, uint32_t* d_hit_query, uint32_t* d_hit_target,
                 uint64_t* d_total, uint8_t* d_any, uint32_t query_id_base, cudaStream_t stream,
-                const uint64_t* d_offset_base) {
+                const uint64_t* d_offset_base, const bcu_filter* filter, const uint8_t* d_qstrand) {
   if (n_q > 0xfffffffeull) { set_error("query batch exceeds 2^32-2 queries"); return BCU_E_LIMIT; }
   if (mode < 0 || mode > 3) { set_error("bad join mode %d", mode); return BCU_E_INVALID; }
   const bool prefix = (mode == kModeCount || mode == kModeFused);
@@ -827,6 +912,16 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
   a.st_ub = nullptr;
   a.cta_total = nullptr;
   a.base_in = d_offset_base;
+  const bool filt = filter && filter->kind != BCU_FILTER_NONE;
+  a.filter_kind = filt ? filter->kind : 0u;
+  a.filter_diff = filt ? filter->diff : 0u;
+  a.filter_use_strand = filt ? filter->use_strand : 0u;
+  a.qstrand = filt ? d_qstrand : nullptr;
+  if (filt && !prefix) { set_error("pair filters are only supported by the count/join entry points"); return BCU_E_INVALID; }
+  if (filt && filter->kind != BCU_FILTER_SV2NL_DUP && filter->kind != BCU_FILTER_SV2NL_INV) {
+    set_error("unknown pair filter kind %u", filter->kind);
+    return BCU_E_INVALID;
+  }
   const uint64_t n_tiles = (n_vq + kCtaTile - 1) / kCtaTile;
   const uint64_t cta_budget = (uint64_t)sm_count(ix->device) * kJoinMinBlocks * 2;  // two waves of CTAs
   if (!prefix) {
@@ -848,10 +943,15 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
   a.st_lb = reinterpret_cast<uint32_t*>(a.cta_total + grid_even);
   a.st_w = a.st_lb + padded;
   a.st_ub = a.st_w + padded;
-  probe_kernel<<<grid, kJoinThreads, 0, stream>>>(a);
+  if (filt) probe_kernel<true><<<grid, kJoinThreads, 0, stream>>>(a);
+  else probe_kernel<false><<<grid, kJoinThreads, 0, stream>>>(a);
   BCU_LAUNCHED();
-  if (mode == kModeFused) emit_kernel<true><<<grid, kJoinThreads, 0, stream>>>(a);
-  else emit_kernel<false><<<grid, kJoinThreads, 0, stream>>>(a);
+  if (mode == kModeFused) {
+    if (filt) emit_kernel<true, true><<<grid, kJoinThreads, 0, stream>>>(a);
+    else emit_kernel<true, false><<<grid, kJoinThreads, 0, stream>>>(a);
+  } else {
+    emit_kernel<false, false><<<grid, kJoinThreads, 0, stream>>>(a);
+  }
   BCU_LAUNCHED();
   BCU_CUDA(cudaFreeAsync(scratch, stream));
   return BCU_OK;

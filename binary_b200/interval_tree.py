@@ -138,6 +138,29 @@ class DeviceIndex:
             return offsets, (hq[: total.value] if want_query_ids else None), ht[: total.value]
         raise _lib.BinaryCudaError(_lib.BCU_E_CAPACITY, "pair capacity still too small after growing")
 
+    def join_filtered(self, qlow, qhigh, qgroup=None, kind: int = _lib.FILTER_SV2NL_DUP, diff: int = 1_000_000,
+                      use_strand: bool = True, qstrand=None, pair_capacity: Optional[int] = None):
+        """``bcu_join_filtered``: the join with sv2nl's DUP / INV ``check_condition`` applied on the device.
+        ``qstrand``: u8 per query, bit0 = strand1 is '+', bit1 = strand2 is '+' (INV with ``use_strand``)."""
+        qlow, qhigh, qgroup = self._queries(qlow, qhigh, qgroup)
+        qs = None if qstrand is None else np.ascontiguousarray(qstrand, dtype=np.uint8)
+        lib = _lib.load()
+        flt = _lib.Filter(kind, diff, int(bool(use_strand)), 0)
+        offsets = np.empty(qlow.size + 1, dtype=np.uint64)
+        cap = int(pair_capacity) if pair_capacity is not None else max(2 * qlow.size, 1 << 16)
+        total = C.c_uint64()
+        for _ in range(2):
+            hq = np.empty(cap, dtype=np.uint32)
+            ht = np.empty(cap, dtype=np.uint32)
+            rc = lib.bcu_join_filtered(self._h, C.byref(flt), qlow.size, _p(qgroup), _p(qlow), _p(qhigh), _p(qs),
+                                       offsets.ctypes.data, cap, hq.ctypes.data, ht.ctypes.data, C.byref(total))
+            if rc == _lib.BCU_E_CAPACITY:
+                cap = total.value
+                continue
+            check(rc)
+            return offsets, hq[: total.value], ht[: total.value]
+        raise _lib.BinaryCudaError(_lib.BCU_E_CAPACITY, "pair capacity still too small after growing")
+
     def any(self, qlow, qhigh, qgroup=None) -> np.ndarray:
         qlow, qhigh, qgroup = self._queries(qlow, qhigh, qgroup)
         out = np.empty(qlow.size, dtype=np.uint8)

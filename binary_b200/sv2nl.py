@@ -5,8 +5,8 @@ Reference being restructured (``/root/reference/standalone/sv2nl``): ``Mapper::m
 record; ``TraMapper`` (``source/mapper.cpp:86-170``) shares one tree over all BND records. Here each of the
 three mappers issues ONE batched join for all chromosomes (chromosome = ``group``; Tra joins on the
 selective breakpoint-proximity condition instead of the raw interval, see below),
-then applies the reference's post-filters (``check_condition``, ``mapper.cpp:50-79,144-156``) vectorised
-on the host over the returned ``(query, target)`` pairs, the duplicate-key rule of ``SV2NL_USE_CACHE``
+with the DUP / INV post-filters (``check_condition``, ``mapper.cpp:50-79``) fused into the join kernels
+(``bcu_join_filtered``) and the TRA conditions (``mapper.cpp:144-156``) vectorised on the host, then the duplicate-key rule of ``SV2NL_USE_CACHE``
 (``mapper.hpp:212-234``) and the writer's formatting (``writer.cpp:21-27``).
 
 Both VCFs are parsed once (``vcf_text.read_vcf``) instead of once per chromosome task. Output lines are
@@ -18,6 +18,7 @@ from typing import Dict, List
 
 import numpy as np
 
+from . import _lib
 from .interval_tree import DeviceIndex
 from .vcf_text import VcfTable, read_vcf
 
@@ -81,9 +82,14 @@ def map_sv2nl(nl: VcfTable, sv: VcfTable, diff: int = 1_000_000, use_strand: boo
             t_chrom, t_pos, t_end, _ = _validated(sv, tsel, swap_chroms=False)  # build_tree validates
             q_chrom, q_pos, q_end, _ = _validated(nl, qsel, swap_chroms=False)
             ix = DeviceIndex.build(t_pos, t_end, cid(t_chrom), device=device)
-            off, hq, ht = ix.join(q_pos, q_end, cid(q_chrom))
+            # check_condition is fused into the join kernels (bcu_join_filtered): rejected pairs are never
+            # counted or written. The host re-evaluation below is then a no-op kept as a cross-check.
+            qstrand = (nl.strand1[qsel].astype(np.uint8) | (nl.strand2[qsel].astype(np.uint8) << 1))
+            off, hq, ht = ix.join_filtered(q_pos, q_end, cid(q_chrom),
+                                           kind=_lib.FILTER_SV2NL_DUP if name == "dup" else _lib.FILTER_SV2NL_INV,
+                                           diff=diff, use_strand=use_strand, qstrand=qstrand)
             ix.close()
-            # check_condition on every raw overlap (vectorised over pairs)
+            n_device = hq.size
             nlp, nle, svp, sve = q_pos[hq], q_end[hq], t_pos[ht], t_end[ht]
             sv_has_nl = (svp <= nlp) & (sve >= nle)                   # is_contained(sv, nl)
             near = (_absdiff(nlp, svp) <= diff) & (_absdiff(nle, sve) <= diff)  # distance_less
@@ -97,6 +103,8 @@ def map_sv2nl(nl: VcfTable, sv: VcfTable, diff: int = 1_000_000, use_strand: boo
                     left = nlp <= svp
                     ok &= np.where(left, s1 & ~s2, ~s1 & s2)
             hq, ht = hq[ok], ht[ok]
+            if hq.size != n_device:
+                raise AssertionError("device filter and host check_condition disagree")
             kept = np.bincount(hq, minlength=qsel.size) > 0
             keys = [f"{nl.chrom[i]}-{int(nl.pos[i])}-{int(nl.svend[i])}" for i in qsel]  # helper.hpp:84-91
             write = _first_per_key_with_hits(keys, kept)

@@ -65,6 +65,22 @@ typedef struct bcu_index_info {
   int32_t reserved;
 } bcu_index_info;
 
+/* Optional pair filter, evaluated on the device on top of the overlap predicate so that rejected pairs are
+ * never counted or written. The two kinds are sv2nl's post-filters (query = validated non-linear record,
+ * target = validated SV record; standalone/sv2nl/source/mapper.cpp in the reference):
+ *   BCU_FILTER_SV2NL_DUP  DupMapper::check_condition  mapper.cpp:50-55:  target contains query and both ends
+ *                         are within `diff` of each other
+ *   BCU_FILTER_SV2NL_INV  InvMapper::check_condition  mapper.cpp:57-79:  neither contains the other, both ends
+ *                         within `diff`, and (if use_strand) strand1 && !strand2 when q.low <= t.low,
+ *                         !strand1 && strand2 otherwise; qstrand[i] bit0 = strand1 is '+', bit1 = strand2 is '+' */
+typedef enum bcu_filter_kind { BCU_FILTER_NONE = 0, BCU_FILTER_SV2NL_DUP = 1, BCU_FILTER_SV2NL_INV = 2 } bcu_filter_kind;
+typedef struct bcu_filter {
+  uint32_t kind;       /* bcu_filter_kind */
+  uint32_t diff;       /* sv2nl --dis */
+  uint32_t use_strand; /* INV only */
+  uint32_t reserved;
+} bcu_filter;
+
 /* ---- library / device ------------------------------------------------------------------------- */
 const char* bcu_version(void);
 const char* bcu_last_error(void);
@@ -102,6 +118,11 @@ int bcu_join(const bcu_index* index, uint64_t n_q, const uint32_t* qgroup, const
              const uint32_t* qhigh, uint64_t* offsets, uint64_t pair_capacity, uint32_t* hit_query,
              uint32_t* hit_target, uint64_t* total);
 int bcu_trim(void);
+/* bcu_join with a pair filter (see bcu_filter). qstrand: n_q bytes, may be NULL unless kind is INV with
+ * use_strand. */
+int bcu_join_filtered(const bcu_index* index, const bcu_filter* filter, uint64_t n_q, const uint32_t* qgroup,
+                      const uint32_t* qlow, const uint32_t* qhigh, const uint8_t* qstrand, uint64_t* offsets,
+                      uint64_t pair_capacity, uint32_t* hit_query, uint32_t* hit_target, uint64_t* total);
 /* any[i] = 1 iff query i overlaps at least one target (shape-independent part of find_overlap). */
 int bcu_query_any(const bcu_index* index, uint64_t n_q, const uint32_t* qgroup,
                   const uint32_t* qlow, const uint32_t* qhigh, uint8_t* any);
@@ -123,6 +144,11 @@ int bcu_join_dev(const bcu_index* index, uint64_t n_q, const uint32_t* d_qgroup,
                  const uint32_t* d_qlow, const uint32_t* d_qhigh, uint64_t* d_offsets,
                  uint64_t pair_capacity, uint32_t* d_hit_query, uint32_t* d_hit_target,
                  uint64_t* d_total, uint32_t query_id_base, void* stream);
+int bcu_join_filtered_dev(const bcu_index* index, const bcu_filter* filter, uint64_t n_q,
+                          const uint32_t* d_qgroup, const uint32_t* d_qlow, const uint32_t* d_qhigh,
+                          const uint8_t* d_qstrand, uint64_t* d_offsets, uint64_t pair_capacity,
+                          uint32_t* d_hit_query, uint32_t* d_hit_target, uint64_t* d_total,
+                          uint32_t query_id_base, void* stream);
 int bcu_query_any_dev(const bcu_index* index, uint64_t n_q, const uint32_t* d_qgroup,
                       const uint32_t* d_qlow, const uint32_t* d_qhigh, uint8_t* d_any,
                       void* stream);

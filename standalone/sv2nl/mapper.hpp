@@ -122,9 +122,11 @@ struct JoinResult {
 };
 
 // one batched join through the C ABI; throws binary::VcfReaderError with the library's message on failure
+// filter == nullptr: plain overlap join; else sv2nl's DUP / INV check_condition runs inside the kernels
 inline JoinResult gpu_join(int device, const std::vector<std::uint32_t>& tg, const std::vector<std::uint32_t>& tl,
                            const std::vector<std::uint32_t>& th, const std::vector<std::uint32_t>& qg,
-                           const std::vector<std::uint32_t>& ql, const std::vector<std::uint32_t>& qh) {
+                           const std::vector<std::uint32_t>& ql, const std::vector<std::uint32_t>& qh,
+                           const bcu_filter* filter = nullptr, const std::vector<std::uint8_t>* qstrand = nullptr) {
   JoinResult r;
   r.offsets.assign(ql.size() + 1, 0);
   if (tl.empty() || ql.empty()) return r;
@@ -136,8 +138,11 @@ inline JoinResult gpu_join(int device, const std::vector<std::uint32_t>& tg, con
   std::uint64_t total = 0, cap = 4 * ql.size() + 1024;
   for (int attempt = 0; attempt < 2; ++attempt) {
     r.targets.resize(cap);
-    int rc = bcu_join(ix, ql.size(), qg.data(), ql.data(), qh.data(), r.offsets.data(), cap, nullptr,
-                      r.targets.data(), &total);
+    int rc = filter ? bcu_join_filtered(ix, filter, ql.size(), qg.data(), ql.data(), qh.data(),
+                                        qstrand ? qstrand->data() : nullptr, r.offsets.data(), cap, nullptr,
+                                        r.targets.data(), &total)
+                    : bcu_join(ix, ql.size(), qg.data(), ql.data(), qh.data(), r.offsets.data(), cap, nullptr,
+                               r.targets.data(), &total);
     if (rc == BCU_E_CAPACITY) { cap = total; continue; }
     if (rc != BCU_OK) { bcu_index_free(ix); check(rc); }
     break;
@@ -193,6 +198,7 @@ inline Sv2nlOutput map_sv2nl(const VcfTable& nl, const VcfTable& sv, const Optio
   for (Kind kind : {Kind{"TDUP", "DUP", false}, Kind{"INV", "INV", true}}) {
     std::vector<Rec> sv_recs, nl_orig, nl_valid;
     std::vector<std::uint32_t> tg, tl, th, qg, ql, qh;
+    std::vector<std::uint8_t> qstrand;
     for (std::size_t i = 0; i < sv.size(); ++i)
       if (sv.svtype[i] == kind.sv_type) {
         sv_recs.push_back(validate_record(record_at(sv, names, i)));  // build_tree validates (mapper.hpp:151)
@@ -203,8 +209,13 @@ inline Sv2nlOutput map_sv2nl(const VcfTable& nl, const VcfTable& sv, const Optio
         nl_orig.push_back(record_at(nl, names, i));
         nl_valid.push_back(validate_record(nl_orig.back()));
         qg.push_back(nl_valid.back().chrom); ql.push_back(nl_valid.back().pos); qh.push_back(nl_valid.back().svend);
+        qstrand.push_back((std::uint8_t)((nl_valid.back().strand1 ? 1 : 0) | (nl_valid.back().strand2 ? 2 : 0)));
       }
-    JoinResult jr = gpu_join(opt.device, tg, tl, th, qg, ql, qh);
+    // check_condition runs on the device (bcu_join_filtered); the host lambdas below re-check the few
+    // surviving pairs, which costs nothing and keeps one definition of the rules next to their citation
+    const bcu_filter filter{kind.inv ? (std::uint32_t)BCU_FILTER_SV2NL_INV : (std::uint32_t)BCU_FILTER_SV2NL_DUP,
+                            opt.diff, opt.use_strand ? 1u : 0u, 0u};
+    JoinResult jr = gpu_join(opt.device, tg, tl, th, qg, ql, qh, &filter, &qstrand);
     auto check_dup = [&](const Rec& n, const Rec& s) {  // mapper.cpp:50-55
       return is_contained(s, n) && distance_less(n, s, opt.diff);
     };

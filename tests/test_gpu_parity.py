@@ -307,3 +307,45 @@ def test_concurrent_host_threads_share_one_index(port_oracle):
         want_off, want_tid = f.query_sorted_pairs(c["ql"][lo:hi], c["qh"][lo:hi], c["qg"][lo:hi])
         off, ht = results[k]
         assert np.array_equal(off, want_off) and np.array_equal(canonical(off, ht)[1], want_tid)
+
+
+def _host_filter(kind, diff, use_strand, ql, qh, tl, th, strand):
+    """numpy twin of sv2nl's check_condition (mapper.cpp:50-79) over pair columns."""
+    ql, qh, tl, th = (x.astype(np.int64) for x in (ql, qh, tl, th))
+    t_has_q = (tl <= ql) & (th >= qh)
+    near = (np.abs(ql - tl) <= diff) & (np.abs(qh - th) <= diff)
+    if kind == 1:
+        return t_has_q & near
+    q_has_t = (ql <= tl) & (qh >= th)
+    ok = ~t_has_q & ~q_has_t & near
+    if use_strand:
+        s1, s2 = (strand & 1).astype(bool), (strand & 2).astype(bool)
+        ok &= np.where(ql <= tl, s1 & ~s2, ~s1 & s2)
+    return ok
+
+
+@pytest.mark.parametrize("kind,use_strand", [(1, True), (2, True), (2, False)])
+@pytest.mark.parametrize("seed,kw", [
+    (41, dict(n_t=20000, n_q=15000, span=400000, max_len=3000, n_groups=4)),                    # short ranges
+    (42, dict(n_t=20000, n_q=6000, span=200000, max_len=60000, n_groups=2)),                     # long ranges
+    (43, dict(n_t=20000, n_q=8000, span=3_000_000, max_len=2000, long_frac=0.01, n_groups=3)),   # length classes
+])
+def test_fused_pair_filters(port_oracle, kind, use_strand, seed, kw):
+    """bcu_join_filtered == (overlap join of the oracle) filtered with check_condition on the host."""
+    c = random_case(seed, **kw)
+    rng = np.random.default_rng(seed)
+    strand = rng.integers(0, 4, c["ql"].size).astype(np.uint8)
+    diff = 2500
+    f = port_oracle.build(c["tl"], c["th"], c["tg"])
+    off, tid = f.query_sorted_pairs(c["ql"], c["qh"], c["qg"], threads=4)
+    qid = np.repeat(np.arange(c["ql"].size, dtype=np.uint32), np.diff(off).astype(np.int64))
+    keep = _host_filter(kind, diff, use_strand, c["ql"][qid], c["qh"][qid], c["tl"][tid], c["th"][tid], strand[qid])
+    want_q, want_t = qid[keep], tid[keep]
+    want_off = np.zeros(c["ql"].size + 1, np.uint64)
+    np.cumsum(np.bincount(want_q, minlength=c["ql"].size), out=want_off[1:])
+    ix = DeviceIndex.build(c["tl"], c["th"], c["tg"])
+    goff, ghq, ght = ix.join_filtered(c["ql"], c["qh"], c["qg"], kind=kind, diff=diff, use_strand=use_strand,
+                                      qstrand=strand)
+    assert 0 < want_q.size < qid.size
+    assert np.array_equal(goff, want_off) and np.array_equal(ghq, want_q)
+    assert np.array_equal(canonical(goff, ght)[1], canonical(want_off, want_t)[1])
