@@ -120,6 +120,12 @@ def ncu_traffic(workload: str):
         return None
 
 
+def cpu_sample_size(workload: str, n_q: int) -> int:
+    """Queries the CPU reference is timed on: ~10-30 core-seconds of work. B (0.65 hits/query, ~1 us per
+    query and core) runs the WHOLE batch; C (83 hits/query, ~500 us per query and core) and D are sampled."""
+    return min(n_q, {"B": 10_000_000, "C": 100_000, "D": 2_000_000}[workload])
+
+
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_run(tg, tl, th, qg, ql, qh, threads=0):
     """Time the reference's CPU path on this box's host cores: oracle/_ref (the unmodified reference
@@ -133,7 +139,7 @@ def cpu_reference_run(tg, tl, th, qg, ql, qh, threads=0):
     build_s = time.perf_counter() - t0
     off, _, query_s = forest.query(ql, qh, qg, threads=threads, want_targets=True)
     return {"value": ql.size / query_s, "unit": UNIT, "cores": threads, "kind": kind,
-            "sample": f"first {ql.size} queries of the workload vs all {tl.size} targets; "
+            "sample": f"first {ql.size} queries of the workload's batch vs all {tl.size} targets; "
                       f"find_overlaps from {threads} threads on one shared read-only forest",
             "build_s": round(build_s, 3), "query_s": round(query_s, 3),
             "hit_pairs_per_sec": float(off[-1]) / query_s}, forest, orc
@@ -145,18 +151,19 @@ def run_reference_arm(args):
         return
     w, n_t, per_gpu = workload_for(args)
     tg, tl, th = w.targets(n_t)
-    sample = args.cpu_sample or min(per_gpu, 2_000_000 if args.workload != "C" else 100_000)
+    sample = args.cpu_sample or cpu_sample_size(args.workload, per_gpu)
     qg, ql, qh = w.queries(0, sample)
     base, forest, orc = cpu_reference_run(tg, tl, th, qg, ql, qh)
     threads = base["cores"]
-    times = []
+    times, pairs = [], 0
     for i in range(args.warmup + args.steps):
-        _, _, s = forest.query(ql, qh, qg, threads=threads, want_targets=True)
+        off, _, s = forest.query(ql, qh, qg, threads=threads, want_targets=True)
+        pairs = int(off[-1])
         if i >= args.warmup:
             times.append(s)
     t = sum(times) / len(times)
     value = sample / t
-    base.update(value=value, query_s=round(t, 4))
+    base.update(value=value, query_s=round(t, 4), hit_pairs_per_sec=pairs / t)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
@@ -337,7 +344,7 @@ def run_ours(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         }
         if not args.no_cpu_baseline and world == 1:
-            sample = args.cpu_sample or min(n_q, 2_000_000 if args.workload != "C" else 100_000)
+            sample = args.cpu_sample or cpu_sample_size(args.workload, n_q)
             base, forest, orc = cpu_reference_run(tg, tl, th, qg[:sample], ql[:sample], qh[:sample])
             line["cpu_baseline"] = base
         else:

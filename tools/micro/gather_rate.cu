@@ -17,9 +17,15 @@ __global__ void gather(const uint4* __restrict__ table, uint64_t entries, uint64
       if (BYTES == 8) {
         uint2 v = reinterpret_cast<const uint2*>(table)[idx];
         acc += v.x; idx = (mix(i + d + 1) + v.y) % entries;
-      } else {
+      } else if (BYTES == 16) {
         uint4 v = table[idx];
         acc += v.x + v.z; idx = (mix(i + d + 1) + v.y) % entries;
+      } else {  // 32 bytes: one 256-bit load (LDG.E.256, sm_100+)
+        uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+        asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+                     : "l"(reinterpret_cast<const char*>(table) + idx * 32));
+        acc += r0 + r2 + r4 + r6 + r7; idx = (mix(i + d + 1) + r1 + r3 + r5) % entries;
       }
     }
   }
@@ -45,6 +51,7 @@ int main() {
     run<8, 1>(t, mb << 20, n, out, "8 B random, independent");
     run<16, 1>(t, mb << 20, n, out, "16 B random, independent");
     run<8, 2>(t, mb << 20, n, out, "8 B random, chain of 2 dependent");
+    run<32, 1>(t, mb << 20, n, out, "32 B random (256-bit), independent");
   }
   return 0;
 }
