@@ -282,10 +282,10 @@ __device__ __forceinline__ void scan_short(const JoinArgs& a, const uint32_t (&q
 // K3/K4, long ranges. A long range [lb, ub) is first trimmed to the EXACT upper bound by its owning lane
 // (the directory's ub is at most about one bin of rows too far; walking back over `low` costs ~1 load), so
 // that every remaining row satisfies t.low <= q.high and only t.high >= q.low is left to test. The warp then
-// streams the SoA column `high` (4 B per row instead of 8) with 128-bit loads, 4 adjacent rows per lane,
-// and works on TWO ranges at a time so their loads overlap. When emitting, the matching `id` column is
-// loaded alongside (no dependent gather), hits are ranked by a warp shuffle scan and written to consecutive
-// slots; the query-id column of a long range is one value and is filled with coalesced stores.
+// streams the SoA column `high` (4 B per row instead of 8), one row per lane, four coalesced loads in
+// flight. When emitting, the matching `id` column is loaded alongside (no dependent gather), a ballot
+// ranks the hits and they are written to consecutive slots; the query-id column of a long range is one
+// value and is filled with coalesced stores.
 struct LongCtx {  // what the long-range path needs, passed BY VALUE into the out-of-line function so
                   // that the callers' per-query arrays stay in registers on the (common) short path
   const uint32_t* high;
@@ -325,112 +325,79 @@ __device__ __forceinline__ uint32_t reaches(uint32_t ql, const uint4& h) {
          ((uint32_t)(ql <= h.w) << 3);
 }
 
-// FILT: the 4 rows' {low, high} come from two 128-bit loads of `lowhigh` and go through accept<true>
-template <bool FILT>
-__device__ __forceinline__ uint32_t long_mask(const LongCtx& c, const LongRange& R, uint32_t r, uint32_t end,
-                                              bool valid) {
-  if (!FILT) {
-    uint4 h = make_uint4(0, 0, 0, 0);
-    if (valid) h = ldg_u4(reinterpret_cast<const uint4*>(c.high) + (r >> 2));
-    return rows_in_range(r, R.lb, end) & reaches(R.ql, h);
-  } else {
-    uint4 p0 = make_uint4(0, 0, 0, 0), p1 = make_uint4(0, 0, 0, 0);
-    if (valid) {
-      const uint4* pairs = reinterpret_cast<const uint4*>(c.lowhigh) + (r >> 1);
-      p0 = ldg_u4(pairs);
-      p1 = ldg_u4(pairs + 1);
-    }
-    const uint32_t m =
-        (uint32_t)accept<true>(c.filter_kind, c.filter_diff, c.filter_use_strand, R.strand, R.ql, R.qh, p0.x, p0.y) |
-        ((uint32_t)accept<true>(c.filter_kind, c.filter_diff, c.filter_use_strand, R.strand, R.ql, R.qh, p0.z, p0.w) << 1) |
-        ((uint32_t)accept<true>(c.filter_kind, c.filter_diff, c.filter_use_strand, R.strand, R.ql, R.qh, p1.x, p1.y) << 2) |
-        ((uint32_t)accept<true>(c.filter_kind, c.filter_diff, c.filter_use_strand, R.strand, R.ql, R.qh, p1.z, p1.w) << 3);
-    return rows_in_range(r, R.lb, end) & m;
+// COUNT only, no filter: 4 adjacent rows per lane per 128-bit load of `high`, TWO loads in flight (256 rows per
+// trip); a lane-local popcount is all that is needed, the warp reduces once per range. (For counting this
+// beats the one-row-per-lane loop below; for emitting it is the other way round, measured.)
+__device__ __forceinline__ uint32_t count_long(const LongCtx& c, int lane, const LongRange& R) {
+  const uint4* high4 = reinterpret_cast<const uint4*>(c.high);
+  uint32_t count = 0;
+  for (uint32_t r = (R.lb & ~3u) + 4u * lane; (r - 4u * lane) < R.ub; r += 256) {
+    const uint32_t r2 = r + 128;
+    uint4 h0 = make_uint4(0, 0, 0, 0), h1 = make_uint4(0, 0, 0, 0);
+    if (r < R.ub) h0 = ldg_u4(high4 + (r >> 2));
+    if (r2 < R.ub) h1 = ldg_u4(high4 + (r2 >> 2));
+    count += __popc(rows_in_range(r, R.lb, R.ub) & reaches(R.ql, h0));
+    count += __popc(rows_in_range(r2, R.lb, R.ub) & reaches(R.ql, h1));
   }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) count += __shfl_xor_sync(0xffffffffu, count, off);
+  return count;
 }
+
+// One long range, scanned by the whole warp: ONE row per lane and trip (the ballot then IS the rank, no
+// shuffle scan), four trips (128 rows) loaded before the first is consumed. Measured on the dense config: fewer instructions per hit than a 4-rows-per-lane / 128-bit-load variant, whose mask
+// building, shuffle scan and 8 predicated stores per trip outweighed the saved load instructions (the
+// kernel is issue- and latency-bound, not L2-bound).
+// FILT: rows are read as {low, high} (8 B per lane) and go through accept<true>.
+constexpr int kTrips = 4;
+struct LongRegs { uint32_t hi[kTrips], lo[kTrips], id[kTrips]; };
 
 template <bool EMIT, bool FILT>
-__device__ __forceinline__ void scan_two_long(const LongCtx& c, int lane, const LongRange& A,
-                                              const LongRange& B, bool has_b, uint32_t& cnt_a,
-                                              uint32_t& cnt_b) {
-  const uint4* id4 = reinterpret_cast<const uint4*>(c.ids);
-  uint32_t ca = 0, cb = 0;  // COUNT: lane-local hit counts; EMIT: hits of the range written so far
-  uint32_t ra = (A.lb & ~3u) + 4u * lane, rb = (B.lb & ~3u) + 4u * lane;
-  const uint32_t end_a = A.ub, end_b = has_b ? B.ub : 0u;
-  // EMIT: 32-bit ranks against a per-range pointer; `lim` = slots of the range that fit the capacity
-  uint32_t* out_a = c.hit_target + A.base;
-  uint32_t* out_b = c.hit_target + B.base;
-  const uint32_t lim_a = c.capacity > A.base ? (uint32_t)min(c.capacity - A.base, (uint64_t)0xffffffffu) : 0u;
-  const uint32_t lim_b = c.capacity > B.base ? (uint32_t)min(c.capacity - B.base, (uint64_t)0xffffffffu) : 0u;
-  while (((ra - 4u * lane) < end_a) | ((rb - 4u * lane) < end_b)) {  // warp-uniform (lane 0's row)
-    const bool va = ra < end_a, vb = rb < end_b;
-    uint4 ia, ib;
-    const uint32_t ma = long_mask<FILT>(c, A, ra, end_a, va);
-    const uint32_t mb = long_mask<FILT>(c, B, rb, end_b, vb);
-    if (EMIT) {
-      ia = ib = make_uint4(0, 0, 0, 0);
-      if (va) ia = ldg_u4(id4 + (ra >> 2));
-      if (vb) ib = ldg_u4(id4 + (rb >> 2));
-    }
-    if (!EMIT) {
-      ca += __popc(ma);
-      cb += __popc(mb);
-    } else {
-      // both streams' lane counts packed in one register: one shuffle scan ranks both
-      const uint32_t c2 = __popc(ma) | (__popc(mb) << 16);
-      uint32_t incl = c2;
+__device__ __forceinline__ void long_preload(const LongCtx& c, int lane, const LongRange& R, uint32_t r0,
+                                             LongRegs& g) {
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
+  for (int t = 0; t < kTrips; ++t) {
+    const uint32_t r = r0 + 32 * t + lane;
+    g.hi[t] = 0;
+    g.lo[t] = 0xffffffffu;
+    g.id[t] = 0;
+    if (r < R.ub) {
+      if (FILT) {
+        const uint2 v = ldg_u2(c.lowhigh + r);
+        g.lo[t] = v.x;
+        g.hi[t] = v.y;
+      } else {
+        g.hi[t] = __ldg(c.high + r);
       }
-      const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
-      const uint32_t excl = incl - c2;
-      uint32_t p = ca + (excl & 0xffffu);
-      if ((ma & 1u) && p < lim_a) out_a[p] = ia.x;
-      p += ma & 1u;
-      if ((ma & 2u) && p < lim_a) out_a[p] = ia.y;
-      p += (ma >> 1) & 1u;
-      if ((ma & 4u) && p < lim_a) out_a[p] = ia.z;
-      p += (ma >> 2) & 1u;
-      if ((ma & 8u) && p < lim_a) out_a[p] = ia.w;
-      p = cb + (excl >> 16);
-      if ((mb & 1u) && p < lim_b) out_b[p] = ib.x;
-      p += mb & 1u;
-      if ((mb & 2u) && p < lim_b) out_b[p] = ib.y;
-      p += (mb >> 1) & 1u;
-      if ((mb & 4u) && p < lim_b) out_b[p] = ib.z;
-      p += (mb >> 2) & 1u;
-      if ((mb & 8u) && p < lim_b) out_b[p] = ib.w;
-      ca += tot & 0xffffu;
-      cb += tot >> 16;
-    }
-    ra += 128;
-    rb += 128;
-  }
-  if (!EMIT) {
-#pragma unroll
-    for (int off = 16; off; off >>= 1) {
-      ca += __shfl_xor_sync(0xffffffffu, ca, off);
-      cb += __shfl_xor_sync(0xffffffffu, cb, off);
-    }
-    cnt_a = ca;
-    cnt_b = cb;
-  } else {
-    // query-id column: one value per range, coalesced fill
-    if (!c.hit_query) return;  // the caller does not want the (redundant with the offsets) query-id column
-    uint32_t* qa = c.hit_query + A.base;
-    const uint32_t na = min(A.cnt, lim_a);
-    for (uint32_t k = lane; k < na; k += 32) qa[k] = A.qid;
-    if (has_b) {
-      uint32_t* qb = c.hit_query + B.base;
-      const uint32_t nb = min(B.cnt, lim_b);
-      for (uint32_t k = lane; k < nb; k += 32) qb[k] = B.qid;
+      if (EMIT) g.id[t] = __ldg(c.ids + r);
     }
   }
 }
 
-// All long ranges of the warp's 128 queries, two at a time. Lane-local inputs per query j (packed in
+// count: COUNT = lane-local hit count; EMIT = hits of the range written so far (warp-uniform)
+template <bool EMIT, bool FILT>
+__device__ __forceinline__ void long_consume(const LongCtx& c, int lane, const LongRange& R, uint32_t r0,
+                                             const LongRegs& g, uint32_t* out, uint32_t lim, uint32_t& count) {
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int t = 0; t < kTrips; ++t) {
+    const uint32_t r = r0 + 32 * t + lane;
+    bool hit = r < R.ub;
+    if (FILT) hit = hit && accept<true>(c.filter_kind, c.filter_diff, c.filter_use_strand, R.strand, R.ql, R.qh,
+                                        g.lo[t], g.hi[t]);
+    else hit = hit && R.ql <= g.hi[t];
+    if (!EMIT) {
+      count += hit;
+    } else {
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      const uint32_t p = count + __popc(bal & lt);
+      if (hit && p < lim) out[p] = g.id[t];
+      count += __popc(bal);
+    }
+  }
+}
+
+// All long ranges of the warp's 128 queries. Lane-local inputs per query j (packed in
 // vectors, by value): bit j of `bigbits`, the exact row range [lb.j, ub.j), ql.j; EMIT also needs cnt.j
 // (from the probe) and the absolute output position pos.j. COUNT returns cnt.j of the long ranges.
 template <bool EMIT, bool FILT>
@@ -444,38 +411,64 @@ __device__ __noinline__ uint4 long_ranges(LongCtx c, int lane, uint32_t bigbits,
   const uint32_t qh[kQPT] = {qh4.x, qh4.y, qh4.z, qh4.w};
   uint32_t cnt[kQPT] = {cnt4.x, cnt4.y, cnt4.z, cnt4.w};
   const uint64_t pos0[kQPT] = {pos_0, pos_1, pos_2, pos_3};
+  if (!EMIT && !FILT) {  // plain counting: 128-bit loads, one range after the other
+#pragma unroll
+    for (int j = 0; j < kQPT; ++j) {
+      unsigned todo = __ballot_sync(0xffffffffu, (bigbits >> j) & 1u);
+      while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        LongRange R;
+        R.lb = __shfl_sync(0xffffffffu, lb[j], src);
+        R.ub = __shfl_sync(0xffffffffu, ub[j], src);
+        R.ql = __shfl_sync(0xffffffffu, ql[j], src);
+        const uint32_t n = count_long(c, lane, R);
+        if (lane == src) cnt[j] = n;
+      }
+    }
+    return make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]);
+  }
+
+  // ---- emit / filtered count: one range after the other. (Software-pipelining the ranges one ahead was
+  // measured and lost: its bookkeeping costs more issue slots than the latency it hides.)
 #pragma unroll
   for (int j = 0; j < kQPT; ++j) {
     unsigned todo = __ballot_sync(0xffffffffu, (bigbits >> j) & 1u);
     while (todo) {
-      const int sa = __ffs(todo) - 1;
+      const int src = __ffs(todo) - 1;
       todo &= todo - 1;
-      const bool has_b = todo != 0;
-      const int sb = has_b ? __ffs(todo) - 1 : sa;
-      if (has_b) todo &= todo - 1;
-      LongRange A, B;
-      A.lb = __shfl_sync(0xffffffffu, lb[j], sa); B.lb = __shfl_sync(0xffffffffu, lb[j], sb);
-      A.ub = __shfl_sync(0xffffffffu, ub[j], sa); B.ub = __shfl_sync(0xffffffffu, ub[j], sb);
-      A.ql = __shfl_sync(0xffffffffu, ql[j], sa); B.ql = __shfl_sync(0xffffffffu, ql[j], sb);
-      A.qh = B.qh = A.strand = B.strand = 0;
+      LongRange R;
+      R.lb = __shfl_sync(0xffffffffu, lb[j], src);
+      R.ub = __shfl_sync(0xffffffffu, ub[j], src);
+      R.ql = __shfl_sync(0xffffffffu, ql[j], src);
+      R.qh = R.strand = 0;
       if (FILT) {
-        A.qh = __shfl_sync(0xffffffffu, qh[j], sa); B.qh = __shfl_sync(0xffffffffu, qh[j], sb);
-        A.strand = (__shfl_sync(0xffffffffu, strand4, sa) >> (8 * j)) & 0xffu;
-        B.strand = (__shfl_sync(0xffffffffu, strand4, sb) >> (8 * j)) & 0xffu;
+        R.qh = __shfl_sync(0xffffffffu, qh[j], src);
+        R.strand = (__shfl_sync(0xffffffffu, strand4, src) >> (8 * j)) & 0xffu;
       }
-      A.qid = c.qid_base + ((vq0 + (uint32_t)sa * kQPT + j) >> c.comp_shift);  // vq0 = warp's first virtual query
-      B.qid = c.qid_base + ((vq0 + (uint32_t)sb * kQPT + j) >> c.comp_shift);
-      A.cnt = B.cnt = 0;
-      A.base = B.base = 0;
+      R.qid = c.qid_base + ((vq0 + (uint32_t)src * kQPT + j) >> c.comp_shift);  // vq0 = warp's first virtual query
+      R.cnt = 0;
+      R.base = 0;
       if (EMIT) {
-        A.cnt = __shfl_sync(0xffffffffu, cnt[j], sa); B.cnt = __shfl_sync(0xffffffffu, cnt[j], sb);
-        A.base = shfl_u64(pos0[j], sa);               B.base = shfl_u64(pos0[j], sb);
+        R.cnt = __shfl_sync(0xffffffffu, cnt[j], src);
+        R.base = shfl_u64(pos0[j], src);
       }
-      uint32_t ca = 0, cb = 0;
-      scan_two_long<EMIT, FILT>(c, lane, A, B, has_b, ca, cb);
+      uint32_t* out = c.hit_target + R.base;  // 32-bit ranks against a per-range pointer
+      const uint32_t lim = c.capacity > R.base ? (uint32_t)min(c.capacity - R.base, (uint64_t)0xffffffffu) : 0u;
+      uint32_t count = 0;
+      for (uint32_t r0 = R.lb; r0 < R.ub; r0 += 32 * kTrips) {
+        LongRegs g;
+        long_preload<EMIT, FILT>(c, lane, R, r0, g);
+        long_consume<EMIT, FILT>(c, lane, R, r0, g, out, lim, count);
+      }
       if (!EMIT) {
-        if (lane == sa) cnt[j] = ca;
-        if (has_b && lane == sb) cnt[j] = cb;
+#pragma unroll
+        for (int off = 16; off; off >>= 1) count += __shfl_xor_sync(0xffffffffu, count, off);
+        if (lane == src) cnt[j] = count;
+      } else if (c.hit_query) {  // the query-id column of a range is one value: coalesced fill
+        uint32_t* q = c.hit_query + R.base;
+        const uint32_t n = min(R.cnt, lim);
+        for (uint32_t k = lane; k < n; k += 32) q[k] = R.qid;
       }
     }
   }
