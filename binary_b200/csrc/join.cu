@@ -381,6 +381,7 @@ __device__ __forceinline__ void long_consume(const LongCtx& c, int lane, const L
   const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
   for (int t = 0; t < kTrips; ++t) {
+    if (t > 0 && r0 + 32 * t >= R.ub) break;  // warp-uniform: do not pay for trips past the end of the range
     const uint32_t r = r0 + 32 * t + lane;
     bool hit = r < R.ub;
     if (FILT) hit = hit && accept<true>(c.filter_kind, c.filter_diff, c.filter_use_strand, R.strand, R.ql, R.qh,
@@ -466,6 +467,7 @@ __device__ __noinline__ uint4 long_ranges(LongCtx c, int lane, uint32_t bigbits,
         for (int off = 16; off; off >>= 1) count += __shfl_xor_sync(0xffffffffu, count, off);
         if (lane == src) cnt[j] = count;
       } else if (c.hit_query) {  // the query-id column of a range is one value: coalesced fill
+        // (fusing this store into the per-hit store above was measured: slower in the emit kernel)
         uint32_t* q = c.hit_query + R.base;
         const uint32_t n = min(R.cnt, lim);
         for (uint32_t k = lane; k < n; k += 32) q[k] = R.qid;
