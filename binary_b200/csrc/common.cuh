@@ -59,6 +59,8 @@ struct GroupDesc {
   uint32_t row_end;
   uint32_t nb;  // number of bins = directory entries = (cmax >> shift) + 1, cmax = max coordinate in group
   uint64_t bin_base;
+  uint32_t proper;  // 1 = every row of the segment has low <= high (enables the O(1) long-range count)
+  uint32_t pad;
 };
 
 constexpr int kMaxSmemGroups = 256;
@@ -92,6 +94,8 @@ struct bcu_index {
   uint32_t* d_runmax = nullptr;      // [n]   running max of high inside the group (max-end array)
   bcu::GroupDesc* d_groups = nullptr;  // [n_comp][n_groups], empty slots have nb == 0
   bcu::DirEntry* d_dir = nullptr;    // [n_bins] see DirEntry
+  uint32_t* d_hs = nullptr;          // [n]   `high` of each segment's rows sorted ASCENDING (same row ranges)
+  uint32_t* d_dirh = nullptr;        // [n_bins] first index of the segment's slice of d_hs with value >= b*W
 };
 
 namespace bcu {

@@ -128,6 +128,58 @@ __global__ void group_probe_kernel(const uint32_t* __restrict__ head_rows, uint3
   cmax[g] = last_low > mh ? last_low : mh;
 }
 
+// keys of the second sort: (segment ordinal << 32) | high; also clears `proper[seg]` for inverted rows
+__global__ void __launch_bounds__(kThreads)
+    high_keys_kernel(const uint2* __restrict__ lowhigh, uint64_t n, const uint32_t* __restrict__ head_rows,
+                     uint32_t n_segs, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                     uint32_t* __restrict__ proper, unsigned long long* varying) {
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t diff = 0;
+  if (r < n) {
+    uint32_t lo = 0, hi = n_segs;  // segment of row r: last head <= r
+    while (hi - lo > 1) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (head_rows[mid] <= r) lo = mid; else hi = mid;
+    }
+    const uint2 t = lowhigh[r];
+    const uint64_t k = ((uint64_t)lo << 32) | t.y;
+    keys[r] = k;
+    vals[r] = (uint32_t)r;
+    if (t.x > t.y) proper[lo] = 0u;
+    diff = k ^ (uint64_t)lowhigh[0].y;  // key of row 0 has segment ordinal 0
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) diff |= __shfl_xor_sync(0xffffffffu, (unsigned long long)diff, off);
+  if ((threadIdx.x & 31) == 0 && diff) atomicOr(varying, (unsigned long long)diff);
+}
+
+__global__ void __launch_bounds__(kThreads)
+    unpack_high_kernel(const uint64_t* __restrict__ keys, uint64_t n, uint32_t* __restrict__ hs) {
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) hs[r] = (uint32_t)keys[r];
+}
+
+// dirh[e] = first index of the segment's slice of hs with hs >= b*W (one thread per directory entry)
+__global__ void __launch_bounds__(kThreads)
+    fill_dirh_kernel(const GroupDesc* __restrict__ groups, uint32_t n_groups, uint32_t shift,
+                     const uint32_t* __restrict__ hs, uint32_t* __restrict__ dirh, uint64_t n_bins) {
+  uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_bins) return;
+  uint32_t lo = 0, hi = n_groups;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (groups[mid].bin_base <= e) lo = mid; else hi = mid;
+  }
+  const GroupDesc g = groups[lo];
+  const uint32_t t0 = (uint32_t)((e - g.bin_base) << shift);
+  uint32_t a = g.row_begin, b = g.row_end;
+  while (a < b) {
+    uint32_t m = a + ((b - a) >> 1);
+    if (hs[m] < t0) a = m + 1; else b = m;
+  }
+  dirh[e] = a;
+}
+
 // one thread per directory entry
 __global__ void __launch_bounds__(kThreads)
     fill_directory_kernel(const GroupDesc* __restrict__ groups, uint32_t n_groups, uint32_t shift,
@@ -184,6 +236,8 @@ static void free_index_members(bcu_index* ix) {
   cudaFreeAsync(ix->d_runmax, nullptr);
   cudaFreeAsync(ix->d_groups, nullptr);
   cudaFreeAsync(ix->d_dir, nullptr);
+  cudaFreeAsync(ix->d_hs, nullptr);
+  cudaFreeAsync(ix->d_dirh, nullptr);
   cudaGetLastError();
 }
 
@@ -358,6 +412,34 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
   }
   const uint32_t n_segs = (uint32_t)heads.size();
 
+  // ---- second sorted view: each segment's `high` values ascending + "all rows proper" flags ----------
+  // With every row proper (low <= high) and a proper query, {rows with high < q.low} is a subset of
+  // {rows with low <= q.high}, so a range's hit count is a difference of two ranks and long ranges
+  // need no counting scan (join.cu, probe). head_rows is sorted on the device at this point.
+  uint32_t* d_proper;
+  BCU_CUDA(tmp.alloc(&d_proper, n_segs));
+  BCU_CUDA(cudaMemsetAsync(d_proper, 0xff, (size_t)n_segs * 4, stream));  // non-zero = proper
+  BCU_CUDA(cudaMemsetAsync(counters, 0, 8, stream));
+  high_keys_kernel<<<grid_rows, kThreads, 0, stream>>>(ix->d_lowhigh, n, head_rows, n_segs, keys_a, vals_a, d_proper,
+                                                      reinterpret_cast<unsigned long long*>(counters));
+  BCU_LAUNCHED();
+  uint64_t varying_h = 0;
+  std::vector<uint32_t> proper(n_segs);
+  BCU_CUDA(cudaMemcpyAsync(&varying_h, counters, 8, cudaMemcpyDeviceToHost, stream));
+  BCU_CUDA(cudaMemcpyAsync(proper.data(), d_proper, (size_t)n_segs * 4, cudaMemcpyDeviceToHost, stream));
+  BCU_CUDA(cudaStreamSynchronize(stream));
+  {
+    uint64_t* hk;
+    uint32_t* hv;
+    uint32_t passes = 0;
+    BCU_TRY(radix_sort_pairs(keys_a, keys_b, vals_a, vals_b, n, varying_h, stream, &hk, &hv, &passes));
+    ix->sort_passes += passes;
+    BCU_CUDA(cudaMallocAsync((void**)&ix->d_hs, (n + 4) * 4, stream));
+    ix->bytes += n * 4;
+    unpack_high_kernel<<<grid_rows, kThreads, 0, stream>>>(hk, n, ix->d_hs);
+    BCU_LAUNCHED();
+  }
+
   // ---- bin width: smallest shift whose directory stays within ~bin_factor entries per target ----
   const double factor = env_double("BCU_BIN_FACTOR", 2.0);
   const uint64_t budget = std::max<uint64_t>((uint64_t)(factor * (double)n), 1024) + 2ull * n_segs;
@@ -374,7 +456,7 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
   for (uint32_t c = 0; c < n_comp; ++c)
     for (uint32_t g = 0; g < n_groups; ++g) {
       GroupDesc& d = table[(size_t)c * n_groups + g];
-      d.gval = gval[g]; d.row_begin = d.row_end = 0; d.nb = 0; d.bin_base = 0;
+      d.gval = gval[g]; d.row_begin = d.row_end = 0; d.nb = 0; d.bin_base = 0; d.proper = 0; d.pad = 0;
     }
   n_bins = 0;
   for (uint32_t s = 0; s < n_segs; ++s) {
@@ -384,6 +466,8 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
     d.row_end = (s + 1 < n_segs) ? heads[s + 1] : (uint32_t)n;
     d.nb = (uint32_t)(((uint64_t)cmax[s] >> shift) + 1);
     d.bin_base = n_bins;
+    d.proper = proper[s] ? 1u : 0u;
+    d.pad = 0;
     n_bins += (uint64_t)d.nb;
     const uint32_t comp = (uint32_t)(seg[s] >> 32);
     const uint32_t g = (uint32_t)(std::lower_bound(gval.begin(), gval.end(), d.gval) - gval.begin());
@@ -405,6 +489,11 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
                            cudaMemcpyHostToDevice, stream));
   fill_directory_kernel<<<(unsigned)((n_bins + kThreads - 1) / kThreads), kThreads, 0, stream>>>(
       d_segs, n_segs, shift, ix->d_lowhigh, ix->d_runmax, ix->d_dir, n_bins);
+  BCU_LAUNCHED();
+  BCU_CUDA(cudaMallocAsync((void**)&ix->d_dirh, n_bins * 4, stream));
+  ix->bytes += n_bins * 4;
+  fill_dirh_kernel<<<(unsigned)((n_bins + kThreads - 1) / kThreads), kThreads, 0, stream>>>(
+      d_segs, n_segs, shift, ix->d_hs, ix->d_dirh, n_bins);
   BCU_LAUNCHED();
   BCU_CUDA(cudaStreamSynchronize(stream));  // host vectors are temporaries
   return BCU_OK;

@@ -59,6 +59,8 @@ struct JoinArgs {
   const uint32_t* __restrict__ high;  // SoA copy of lowhigh[].y, padded: the long-range path streams it
   const uint32_t* __restrict__ ids;
   const DirEntry* __restrict__ dir;
+  const uint32_t* __restrict__ hs;    // each segment's `high` values ascending (O(1) long-range count)
+  const uint32_t* __restrict__ dirh;  // per directory entry: first index of hs with value >= b*W
   const GroupDesc* __restrict__ groups;
   uint32_t n_groups;
   uint32_t shift;
@@ -83,6 +85,8 @@ struct JoinArgs {
   uint32_t* st_w;       // [same] probe state: hit bitmask, or kBigFlag | hit count
   uint32_t* st_ub;      // [same] probe state of LONG ranges only: exact end row (untouched otherwise)
   uint64_t* cta_total;  // [gridDim.x] hits per chunk
+  uint32_t* big_list;   // [padded n_vq] per chunk, from its first slot on: the virtual queries with LONG ranges
+  uint32_t rank_min;    // a warp step with at least this many long ranges lists them, else scans them in place
   const uint64_t* base_in;  // optional: offset of the batch's first pair (chunked host pipeline)
   // optional pair filter applied ON TOP of the overlap predicate (sv2nl's check_condition, fused)
   uint32_t filter_kind;     // bcu_filter_kind
@@ -95,6 +99,8 @@ struct GroupTables {
   uint32_t g_val[kMaxSmemGroups];  // sorted group values (binary-search mode)
   uint32_t g_nb[kMaxSmemGroups];
   uint64_t g_base[kMaxSmemGroups];
+  uint32_t g_re[kMaxSmemGroups];     // row_end of the segment
+  uint8_t g_proper[kMaxSmemGroups];  // every row of the segment has low <= high
   uint16_t g_map[kDirectGroups];   // group value -> descriptor index, 0xffff = absent (direct mode)
 };
 
@@ -163,6 +169,8 @@ __device__ __forceinline__ void load_group_tables(const JoinArgs& a, GroupTables
       tb.g_val[g] = d.gval;
       tb.g_nb[g] = d.nb;
       tb.g_base[g] = d.bin_base;
+      tb.g_re[g] = d.row_end;
+      tb.g_proper[g] = (uint8_t)d.proper;
       if (direct && g < a.n_groups) tb.g_map[d.gval] = (uint16_t)g;
     }
   }
@@ -312,6 +320,41 @@ __device__ __forceinline__ uint32_t exact_upper_bound(const JoinArgs& a, uint32_
   uint32_t u = lb + len;
   while (u > lb && a.lowhigh[u - 1].x > qh) --u;
   return u;
+}
+
+// O(1) hit count of a long range by rank arithmetic. When every row of the segment is proper (low <= high)
+// and so is the query, the rows that end before the query, {high < q.low}, are a subset of the rows that
+// start in time, {low <= q.high}; hence
+//     hits = #{low <= q.high} - #{high < q.low} = (ub_exact - row_begin) - (i - row_begin) = ub_exact - i,
+// with i = lower_bound of q.low in the segment's ascending `high` view (directory dirh + a short walk).
+// Returns kNoRank when the shortcut does not apply (inverted rows or query): the caller scans instead.
+constexpr uint32_t kNoRank = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t count_by_ranks(const JoinArgs& a, const GroupTables& tb, uint32_t slot,
+                                                   uint32_t ql, uint32_t qh, uint32_t qg, uint32_t ub_exact) {
+  if (ql > qh) return kNoRank;
+  const bool in_smem = a.n_groups * a.n_comp <= (uint32_t)kMaxSmemGroups;
+  const bool direct = in_smem && a.max_gval < (uint32_t)kDirectGroups;
+  uint32_t gi;
+  if (direct) {
+    gi = tb.g_map[qg];  // the probe found candidates, so the group exists and qg is in range
+  } else {
+    uint32_t lo = 0, hi = a.n_groups;
+    while (lo < hi) {
+      uint32_t mid = (lo + hi) >> 1;
+      const uint32_t v = in_smem ? tb.g_val[mid] : a.groups[mid].gval;
+      if (v < qg) lo = mid + 1; else hi = mid;
+    }
+    gi = lo;
+  }
+  gi += slot * a.n_groups;
+  const bool proper = in_smem ? tb.g_proper[gi] != 0 : a.groups[gi].proper != 0;
+  if (!proper) return kNoRank;
+  const uint64_t bin_base = in_smem ? tb.g_base[gi] : a.groups[gi].bin_base;
+  const uint32_t row_end = in_smem ? tb.g_re[gi] : a.groups[gi].row_end;
+  uint32_t i = a.dirh[bin_base + (ql >> a.shift)];  // b_lo < nb: the range is non-empty
+  while (i < row_end && a.hs[i] < ql) ++i;
+  return ub_exact > i ? ub_exact - i : 0u;
 }
 
 // bits k = 0..3: row r+k lies inside [lb, ub)
@@ -556,17 +599,23 @@ __device__ __forceinline__ void emit_short(const JoinArgs& a, StageBuffers& st, 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K3: probe. No barriers inside the chunk loop.
+// K3: probe. No barriers inside the chunk loop, and nothing is called from it: a long range (> kScalarMax
+// rows) is either scanned in place by the warp (few per step) or only leaves its marker and inexact end in
+// the state and its query number in the chunk's list for phase 2
+// (with 64 registers per thread, any out-of-line call in this loop made ptxas spill the prefetched queries).
 template <bool FILT>
 __global__ void __launch_bounds__(kJoinThreads, kProbeMinBlocks) probe_kernel(const JoinArgs a) {
   __shared__ GroupTables tb;
   __shared__ uint64_t s_warp_total[kJoinWarps];
+  __shared__ uint32_t s_big;  // long ranges listed by this CTA so far
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  load_group_tables(a, tb);
+  if (tid == 0) s_big = 0;
+  load_group_tables(a, tb);  // ends with a barrier
 
   const uint64_t chunk_begin = (uint64_t)blockIdx.x * a.chunk;
   const uint64_t chunk_end = min(chunk_begin + (uint64_t)a.chunk, (uint64_t)a.n_vq);
-  uint64_t acc = 0;  // hits of this lane's queries over the whole chunk
+  uint32_t* const list = a.big_list + chunk_begin;
+  uint64_t acc = 0;  // hits of this lane's queries over the whole chunk (short ranges)
 
   uint64_t w0 = chunk_begin + (uint64_t)warp * kWarpTile;
   uint32_t nql[kQPT], nqh[kQPT], nqg[kQPT];  // prefetched queries of the next step
@@ -598,22 +647,79 @@ __global__ void __launch_bounds__(kJoinThreads, kProbeMinBlocks) probe_kernel(co
       ub[j] = lb[j] + len[j];
     }
     if (__any_sync(0xffffffffu, lane_big)) {
+      // (a filter must see every pair: it always scans)
+      if (!FILT && (uint32_t)__popc(__ballot_sync(0xffffffffu, lane_big)) >= a.rank_min) {
+        // many long ranges in this step: list them for phase 2, which handles one per LANE (warp scan of the
+        // per-lane counts, one shared-memory atomic per warp and step)
+        const uint32_t n_big = (uint32_t)big[0] + big[1] + big[2] + big[3];
+        uint32_t incl = n_big;
 #pragma unroll
-      for (int j = 0; j < kQPT; ++j)
-        if (big[j]) ub[j] = exact_upper_bound(a, lb[j], len[j], qh[j]);
-      const uint4 c4 = long_ranges<false, FILT>(
-          long_ctx(a), lane, pack_bits(big), make_uint4(lb[0], lb[1], lb[2], lb[3]),
-          make_uint4(ub[0], ub[1], ub[2], ub[3]), make_uint4(ql[0], ql[1], ql[2], ql[3]), make_uint4(0, 0, 0, 0), 0,
-          0, 0, 0, 0, make_uint4(qh[0], qh[1], qh[2], qh[3]),
-          strand[0] | (strand[1] << 8) | (strand[2] << 16) | (strand[3] << 24));
-      const uint32_t cl[kQPT] = {c4.x, c4.y, c4.z, c4.w};
+        for (int off = 1; off < 32; off <<= 1) {
+          const uint32_t y = __shfl_up_sync(0xffffffffu, incl, off);
+          if (lane >= off) incl += y;
+        }
+        uint32_t base = 0;
+        if (lane == 31) base = atomicAdd(&s_big, incl);
+        base = __shfl_sync(0xffffffffu, base, 31) + incl - n_big;
 #pragma unroll
-      for (int j = 0; j < kQPT; ++j)
-        if (big[j]) { acc += cl[j]; w[j] = kBigFlag | cl[j]; a.st_ub[q0 + j] = ub[j]; }
+        for (int j = 0; j < kQPT; ++j)
+          if (big[j]) {
+            list[base++] = q0 + j;
+            a.st_ub[q0 + j] = ub[j];
+            w[j] = kBigFlag;
+          }
+      } else {
+        // few: the whole warp scans them here, one after the other
+#pragma unroll
+        for (int j = 0; j < kQPT; ++j)
+          if (big[j]) ub[j] = exact_upper_bound(a, lb[j], len[j], qh[j]);
+        const uint4 c4 = long_ranges<false, FILT>(
+            long_ctx(a), lane, pack_bits(big), make_uint4(lb[0], lb[1], lb[2], lb[3]),
+            make_uint4(ub[0], ub[1], ub[2], ub[3]), make_uint4(ql[0], ql[1], ql[2], ql[3]), make_uint4(0, 0, 0, 0),
+            0, 0, 0, 0, 0, make_uint4(qh[0], qh[1], qh[2], qh[3]),
+            strand[0] | (strand[1] << 8) | (strand[2] << 16) | (strand[3] << 24));
+        const uint32_t cl[kQPT] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+        for (int j = 0; j < kQPT; ++j)
+          if (big[j]) { acc += cl[j]; w[j] = kBigFlag | cl[j]; a.st_ub[q0 + j] = ub[j]; }
+      }
     }
     // state: 8 bytes per query, 128-bit stores (the arrays are padded to a multiple of kCtaTile)
     *reinterpret_cast<uint4*>(a.st_lb + q0) = make_uint4(lb[0], lb[1], lb[2], lb[3]);
     *reinterpret_cast<uint4*>(a.st_w + q0) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  // Phase 2: the long ranges this CTA listed, one per LANE: exact end of the candidate rows, then the hit
+  // count by rank arithmetic (count_by_ranks); the ranges whose segment does not allow it are scanned by
+  // the whole warp. The other CTAs of the SM are still in their phase 1, which hides these dependent loads.
+  if (!FILT) {
+    __syncthreads();
+    const uint32_t n_list = s_big;
+    for (uint32_t i0 = warp * 32; i0 < n_list; i0 += kJoinThreads) {  // warp-uniform trip count
+      const bool have = i0 + lane < n_list;
+      uint32_t v = 0, lb = 0, ub = 0, ql = 0, qh = 0, cnt = 0;
+      bool scan = false;
+      if (have) {
+        v = list[i0 + lane];
+        const uint32_t q = v >> a.comp_shift;
+        lb = a.st_lb[v];
+        ql = a.qlow[q];
+        qh = a.qhigh[q];
+        ub = exact_upper_bound(a, lb, a.st_ub[v] - lb, qh);
+        a.st_ub[v] = ub;
+        cnt = count_by_ranks(a, tb, v & (a.n_comp - 1u), ql, qh, a.qgroup ? a.qgroup[q] : 0u, ub);
+        scan = cnt == kNoRank;
+      }
+      if (__any_sync(0xffffffffu, scan)) {
+        const uint4 c4 = long_ranges<false, false>(long_ctx(a), lane, scan ? 1u : 0u, make_uint4(lb, 0, 0, 0),
+                                                   make_uint4(ub, 0, 0, 0), make_uint4(ql, 0, 0, 0),
+                                                   make_uint4(0, 0, 0, 0), 0, 0, 0, 0, 0, make_uint4(qh, 0, 0, 0), 0);
+        if (scan) cnt = c4.x;
+      }
+      if (have) {
+        a.st_w[v] = kBigFlag | cnt;
+        acc += cnt;
+      }
+    }
   }
 #pragma unroll
   for (int off = 16; off; off >>= 1) acc += shfl_u64(acc, lane ^ off);
@@ -858,6 +964,16 @@ static int sm_count(int device) {
   return sms;
 }
 
+// BCU_RANK_MIN (tuning): long ranges per 32-lane probe step from which they go to the per-lane rank pass
+static uint32_t rank_min_lanes() {
+  static const uint32_t v = [] {
+    const char* e = getenv("BCU_RANK_MIN");
+    const long x = e ? atol(e) : 8;
+    return (uint32_t)(x < 1 ? 1 : (x > 33 ? 33 : x));
+  }();
+  return v;
+}
+
 int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_qgroup,
                 const uint32_t* d_qlow, const uint32_t* d_qhigh, uint64_t* d_offsets,
                 uint64_t pair_capacity, uint32_t* d_hit_query, uint32_t* d_hit_target,
@@ -879,6 +995,8 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
   a.high = ix->d_high;
   a.ids = ix->d_id;
   a.dir = ix->d_dir;
+  a.hs = ix->d_hs;
+  a.dirh = ix->d_dirh;
   a.groups = ix->d_groups;
   a.n_groups = ix->n_groups;
   a.shift = ix->shift;
@@ -906,6 +1024,8 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
   a.st_w = nullptr;
   a.st_ub = nullptr;
   a.cta_total = nullptr;
+  a.big_list = nullptr;
+  a.rank_min = rank_min_lanes();
   a.base_in = d_offset_base;
   const bool filt = filter && filter->kind != BCU_FILTER_NONE;
   a.filter_kind = filt ? filter->kind : 0u;
@@ -933,11 +1053,12 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
   const uint64_t padded = n_tiles * kCtaTile;
   void* scratch = nullptr;
   const uint64_t grid_even = ((uint64_t)grid + 1) & ~1ull;  // keeps the state arrays 16-byte aligned
-  BCU_CUDA(cudaMallocAsync(&scratch, padded * 12 + grid_even * 8, stream));
+  BCU_CUDA(cudaMallocAsync(&scratch, padded * 16 + grid_even * 8, stream));
   a.cta_total = reinterpret_cast<uint64_t*>(scratch);
   a.st_lb = reinterpret_cast<uint32_t*>(a.cta_total + grid_even);
   a.st_w = a.st_lb + padded;
   a.st_ub = a.st_w + padded;
+  a.big_list = a.st_ub + padded;
   if (filt) probe_kernel<true><<<grid, kJoinThreads, 0, stream>>>(a);
   else probe_kernel<false><<<grid, kJoinThreads, 0, stream>>>(a);
   BCU_LAUNCHED();
