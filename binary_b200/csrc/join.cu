@@ -86,7 +86,7 @@ struct JoinArgs {
   uint32_t* st_ub;      // [same] probe state of LONG ranges only: exact end row (untouched otherwise)
   uint64_t* cta_total;  // [gridDim.x] hits per chunk
   uint32_t* big_list;   // [padded n_vq] per chunk, from its first slot on: the virtual queries with LONG ranges
-  uint32_t rank_min;    // a warp step with at least this many long ranges lists them, else scans them in place
+  uint32_t* cta_big;    // [gridDim.x] entries of the chunk's list
   const uint64_t* base_in;  // optional: offset of the batch's first pair (chunked host pipeline)
   // optional pair filter applied ON TOP of the overlap predicate (sv2nl's check_condition, fused)
   uint32_t filter_kind;     // bcu_filter_kind
@@ -275,15 +275,23 @@ __device__ __forceinline__ void scan_short(const JoinArgs& a, const uint32_t (&q
     if (len[j] > kScalarMax) mask[j] = 0;
     else if (len[j] > max_short) max_short = len[j];
   }
+  uint32_t n[kQPT];  // rows of the short range (0 for a long one)
+#pragma unroll
+  for (int j = 0; j < kQPT; ++j) n[j] = len[j] <= kScalarMax ? len[j] : 0u;
   for (uint32_t k = kInlineRows; k < max_short; ++k) {
+    // all four loads are issued before the first is used (written any other way, ptxas under the 64-register
+    // cap has been seen to give them one destination register, i.e. to serialise them)
+    uint2 t[kQPT];
 #pragma unroll
     for (int j = 0; j < kQPT; ++j) {
-      if (k < len[j] && len[j] <= kScalarMax) {
-        const uint2 t = ldg_u2(a.lowhigh + lb[j] + k);
-        mask[j] |= (uint32_t)accept<FILT>(a.filter_kind, a.filter_diff, a.filter_use_strand, strand[j], ql[j],
-                                          qh[j], t.x, t.y) << k;
-      }
+      t[j] = make_uint2(0xffffffffu, 0u);
+      if (k < n[j]) t[j] = ldg_u2(a.lowhigh + lb[j] + k);
     }
+#pragma unroll
+    for (int j = 0; j < kQPT; ++j)
+      if (k < n[j])
+        mask[j] |= (uint32_t)accept<FILT>(a.filter_kind, a.filter_diff, a.filter_use_strand, strand[j], ql[j],
+                                          qh[j], t[j].x, t[j].y) << k;
   }
 }
 
@@ -599,10 +607,9 @@ __device__ __forceinline__ void emit_short(const JoinArgs& a, StageBuffers& st, 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K3: probe. No barriers inside the chunk loop, and nothing is called from it: a long range (> kScalarMax
-// rows) is either scanned in place by the warp (few per step) or only leaves its marker and inexact end in
-// the state and its query number in the chunk's list for phase 2
-// (with 64 registers per thread, any out-of-line call in this loop made ptxas spill the prefetched queries).
+// K3: probe. No barriers inside the chunk loop. A long range (> kScalarMax rows) only leaves its marker and
+// inexact end in the state and its query number in the chunk's list, for phase 2 below and for K4b; under a
+// filter (which must see every pair) the warp scans it in place instead.
 template <bool FILT>
 __global__ void __launch_bounds__(kJoinThreads, kProbeMinBlocks) probe_kernel(const JoinArgs a) {
   __shared__ GroupTables tb;
@@ -647,10 +654,8 @@ __global__ void __launch_bounds__(kJoinThreads, kProbeMinBlocks) probe_kernel(co
       ub[j] = lb[j] + len[j];
     }
     if (__any_sync(0xffffffffu, lane_big)) {
-      // (a filter must see every pair: it always scans)
-      if (!FILT && (uint32_t)__popc(__ballot_sync(0xffffffffu, lane_big)) >= a.rank_min) {
-        // many long ranges in this step: list them for phase 2, which handles one per LANE (warp scan of the
-        // per-lane counts, one shared-memory atomic per warp and step)
+      if (!FILT) {
+        // list them (warp scan of the per-lane counts, one shared-memory atomic per warp and step)
         const uint32_t n_big = (uint32_t)big[0] + big[1] + big[2] + big[3];
         uint32_t incl = n_big;
 #pragma unroll
@@ -669,7 +674,7 @@ __global__ void __launch_bounds__(kJoinThreads, kProbeMinBlocks) probe_kernel(co
             w[j] = kBigFlag;
           }
       } else {
-        // few: the whole warp scans them here, one after the other
+        // filtered: the whole warp scans them here, one after the other
 #pragma unroll
         for (int j = 0; j < kQPT; ++j)
           if (big[j]) ub[j] = exact_upper_bound(a, lb[j], len[j], qh[j]);
@@ -730,6 +735,7 @@ __global__ void __launch_bounds__(kJoinThreads, kProbeMinBlocks) probe_kernel(co
 #pragma unroll
     for (int w = 0; w < kJoinWarps; ++w) t += s_warp_total[w];
     a.cta_total[blockIdx.x] = t;
+    a.cta_big[blockIdx.x] = FILT ? 0u : s_big;
   }
 }
 
@@ -840,6 +846,7 @@ __global__ void __launch_bounds__(kJoinThreads, kEmitMinBlocks) emit_kernel(cons
   // Kept out of the loop above so that its register needs (and the out-of-line call) do not spill into
   // the hot short-range path. Everything comes from the probe state, the query column and the offsets
   // this very thread wrote a moment ago.
+  if (!FILT) return;  // without a filter the long ranges are listed: K4b emits them
   for (uint64_t t0 = chunk_begin; t0 < chunk_end; t0 += kCtaTile) {
     const uint32_t w0 = (uint32_t)t0 + (uint32_t)warp * kWarpTile;
     const uint32_t q0 = w0 + (uint32_t)lane * kQPT;
@@ -870,6 +877,71 @@ __global__ void __launch_bounds__(kJoinThreads, kEmitMinBlocks) emit_kernel(cons
                             make_uint4(bub[0], bub[1], bub[2], bub[3]), make_uint4(ql[0], ql[1], ql[2], ql[3]),
                             make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]), pos[0], pos[1], pos[2], pos[3], w0,
                             make_uint4(qh[0], qh[1], qh[2], qh[3]), strand4);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K4b: the pairs of the listed long ranges (no filter). Same grid and chunks as K3: a CTA walks its own
+// chunk's list, 32 entries per warp and round (one per lane), then the warp streams the ranges one after
+// the other (long_preload / long_consume). A kernel of its own because this part is bound by the latency
+// of one range after the other per warp: it needs far fewer registers than K4, so twice the warps per SM.
+#ifndef BCU_LONG_MB
+#define BCU_LONG_MB 6
+#endif
+constexpr int kLongMinBlocks = BCU_LONG_MB;
+__global__ void __launch_bounds__(kJoinThreads, kLongMinBlocks) emit_long_kernel(const JoinArgs a) {
+  const uint32_t n_list = a.cta_big[blockIdx.x];
+  if (n_list == 0) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t* const list = a.big_list + (uint64_t)blockIdx.x * a.chunk;
+  const LongCtx c = long_ctx(a);
+  for (uint32_t i0 = warp * 32; i0 < n_list; i0 += kJoinThreads) {  // warp-uniform trip count
+    const bool have = i0 + lane < n_list;
+    LongRange mine;
+    mine.lb = mine.ub = mine.ql = mine.qh = mine.strand = mine.cnt = mine.qid = 0;
+    mine.base = 0;
+    if (have) {
+      const uint32_t v = list[i0 + lane], q = v >> a.comp_shift;
+      mine.lb = a.st_lb[v];
+      mine.ub = a.st_ub[v];
+      mine.ql = a.qlow[q];
+      mine.cnt = a.st_w[v] & ~kBigFlag;
+      mine.qid = a.qid_base + q;
+      uint64_t pos = a.offsets[q];  // + the hits of the query's earlier length-class slots
+      for (uint32_t u = v & ~(a.n_comp - 1u); u < v; ++u) {
+        const uint32_t w = a.st_w[u];
+        pos += (w & kBigFlag) ? (w & ~kBigFlag) : (uint32_t)__popc(w);
+      }
+      mine.base = pos;
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, have && mine.cnt != 0);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      LongRange R;
+      R.lb = __shfl_sync(0xffffffffu, mine.lb, src);
+      R.ub = __shfl_sync(0xffffffffu, mine.ub, src);
+      R.ql = __shfl_sync(0xffffffffu, mine.ql, src);
+      R.cnt = __shfl_sync(0xffffffffu, mine.cnt, src);
+      R.qid = __shfl_sync(0xffffffffu, mine.qid, src);
+      R.base = shfl_u64(mine.base, src);
+      R.qh = R.strand = 0;
+      uint32_t* out = c.hit_target + R.base;
+      const uint32_t lim = c.capacity > R.base ? (uint32_t)min(c.capacity - R.base, (uint64_t)0xffffffffu) : 0u;
+      // (measured and not kept: a predicate-free path for whole 128-row blocks, writing the query id next
+      // to each hit instead of the fill below, and 4 rows per lane with 128-bit loads)
+      uint32_t count = 0;
+      for (uint32_t r0 = R.lb; r0 < R.ub; r0 += 32 * kTrips) {
+        LongRegs g;
+        long_preload<true, false>(c, lane, R, r0, g);
+        long_consume<true, false>(c, lane, R, r0, g, out, lim, count);
+      }
+      if (c.hit_query) {  // the query-id column of a range is one value: coalesced fill
+        uint32_t* qcol = c.hit_query + R.base;
+        const uint32_t n = min(R.cnt, lim);
+        for (uint32_t k = lane; k < n; k += 32) qcol[k] = R.qid;
+      }
+    }
   }
 }
 
@@ -964,16 +1036,6 @@ static int sm_count(int device) {
   return sms;
 }
 
-// BCU_RANK_MIN (tuning): long ranges per 32-lane probe step from which they go to the per-lane rank pass
-static uint32_t rank_min_lanes() {
-  static const uint32_t v = [] {
-    const char* e = getenv("BCU_RANK_MIN");
-    const long x = e ? atol(e) : 8;
-    return (uint32_t)(x < 1 ? 1 : (x > 33 ? 33 : x));
-  }();
-  return v;
-}
-
 int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_qgroup,
                 const uint32_t* d_qlow, const uint32_t* d_qhigh, uint64_t* d_offsets,
                 uint64_t pair_capacity, uint32_t* d_hit_query, uint32_t* d_hit_target,
@@ -1025,7 +1087,7 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
   a.st_ub = nullptr;
   a.cta_total = nullptr;
   a.big_list = nullptr;
-  a.rank_min = rank_min_lanes();
+  a.cta_big = nullptr;
   a.base_in = d_offset_base;
   const bool filt = filter && filter->kind != BCU_FILTER_NONE;
   a.filter_kind = filt ? filter->kind : 0u;
@@ -1053,18 +1115,23 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
   const uint64_t padded = n_tiles * kCtaTile;
   void* scratch = nullptr;
   const uint64_t grid_even = ((uint64_t)grid + 1) & ~1ull;  // keeps the state arrays 16-byte aligned
-  BCU_CUDA(cudaMallocAsync(&scratch, padded * 16 + grid_even * 8, stream));
+  BCU_CUDA(cudaMallocAsync(&scratch, padded * 16 + grid_even * 12, stream));
   a.cta_total = reinterpret_cast<uint64_t*>(scratch);
   a.st_lb = reinterpret_cast<uint32_t*>(a.cta_total + grid_even);
   a.st_w = a.st_lb + padded;
   a.st_ub = a.st_w + padded;
   a.big_list = a.st_ub + padded;
+  a.cta_big = a.big_list + padded;
   if (filt) probe_kernel<true><<<grid, kJoinThreads, 0, stream>>>(a);
   else probe_kernel<false><<<grid, kJoinThreads, 0, stream>>>(a);
   BCU_LAUNCHED();
   if (mode == kModeFused) {
     if (filt) emit_kernel<true, true><<<grid, kJoinThreads, 0, stream>>>(a);
     else emit_kernel<true, false><<<grid, kJoinThreads, 0, stream>>>(a);
+    if (!filt) {
+      BCU_LAUNCHED();
+      emit_long_kernel<<<grid, kJoinThreads, 0, stream>>>(a);
+    }
   } else {
     emit_kernel<false, false><<<grid, kJoinThreads, 0, stream>>>(a);
   }
