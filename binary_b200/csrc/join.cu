@@ -606,6 +606,11 @@ __device__ __forceinline__ void emit_short(const JoinArgs& a, StageBuffers& st, 
   }
 }
 
+// Programmatic dependent launch (sm_90+): the producer lets the next kernel of the stream be placed early,
+// the consumer waits here until the producer grid has completed and its writes are visible.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 // ---------------------------------------------------------------------------------------------------
 // K3: probe. No barriers inside the chunk loop. A long range (> kScalarMax rows) only leaves its marker and
 // inexact end in the state and its query number in the chunk's list, for phase 2 below and for K4b; under a
@@ -617,6 +622,7 @@ __global__ void __launch_bounds__(kJoinThreads, kProbeMinBlocks) probe_kernel(co
   __shared__ uint32_t s_big;  // long ranges listed by this CTA so far
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_big = 0;
+  grid_launch_dependents();
   load_group_tables(a, tb);  // ends with a barrier
 
   const uint64_t chunk_begin = (uint64_t)blockIdx.x * a.chunk;
@@ -747,6 +753,8 @@ __global__ void __launch_bounds__(kJoinThreads, kEmitMinBlocks) emit_kernel(cons
   __shared__ uint64_t s_warp_total[2][kJoinWarps];
   __shared__ uint64_t s_red[kJoinWarps];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  grid_dependency_wait();    // K3's state and totals
+  grid_launch_dependents();  // K4b may be placed behind this grid
 
   // global base of this chunk = hits of all chunks before it
   uint64_t part = 0;
@@ -890,6 +898,7 @@ __global__ void __launch_bounds__(kJoinThreads, kEmitMinBlocks) emit_kernel(cons
 #endif
 constexpr int kLongMinBlocks = BCU_LONG_MB;
 __global__ void __launch_bounds__(kJoinThreads, kLongMinBlocks) emit_long_kernel(const JoinArgs a) {
+  grid_dependency_wait();  // K4's offsets (and through it K3's lists)
   const uint32_t n_list = a.cta_big[blockIdx.x];
   if (n_list == 0) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1036,6 +1045,23 @@ static int sm_count(int device) {
   return sms;
 }
 
+static int launch_dependent(void (*kernel)(const JoinArgs), unsigned grid, cudaStream_t stream,
+                            const JoinArgs& a) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kJoinThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  BCU_CUDA(cudaLaunchKernelEx(&cfg, kernel, a));
+  BCU_LAUNCHED();
+  return BCU_OK;
+}
+
 int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_qgroup,
                 const uint32_t* d_qlow, const uint32_t* d_qhigh, uint64_t* d_offsets,
                 uint64_t pair_capacity, uint32_t* d_hit_query, uint32_t* d_hit_target,
@@ -1125,17 +1151,15 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
   if (filt) probe_kernel<true><<<grid, kJoinThreads, 0, stream>>>(a);
   else probe_kernel<false><<<grid, kJoinThreads, 0, stream>>>(a);
   BCU_LAUNCHED();
+  // K4 / K4b are launched as programmatic dependents: their CTAs are placed while the previous kernel
+  // drains and block in grid_dependency_wait() until it has completed (hides the launch gaps)
   if (mode == kModeFused) {
-    if (filt) emit_kernel<true, true><<<grid, kJoinThreads, 0, stream>>>(a);
-    else emit_kernel<true, false><<<grid, kJoinThreads, 0, stream>>>(a);
-    if (!filt) {
-      BCU_LAUNCHED();
-      emit_long_kernel<<<grid, kJoinThreads, 0, stream>>>(a);
-    }
+    if (filt) BCU_TRY(launch_dependent(emit_kernel<true, true>, grid, stream, a));
+    else BCU_TRY(launch_dependent(emit_kernel<true, false>, grid, stream, a));
+    if (!filt) BCU_TRY(launch_dependent(emit_long_kernel, grid, stream, a));
   } else {
-    emit_kernel<false, false><<<grid, kJoinThreads, 0, stream>>>(a);
+    BCU_TRY(launch_dependent(emit_kernel<false, false>, grid, stream, a));
   }
-  BCU_LAUNCHED();
   BCU_CUDA(cudaFreeAsync(scratch, stream));
   return BCU_OK;
 }
