@@ -62,6 +62,9 @@ SIGNATURES = {
     "bcu_query_scatter_dev": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp, vp, vp, vp]),
     "bcu_join_dev": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp, C.c_uint64, vp, vp, vp, C.c_uint32, vp]),
     "bcu_query_any_dev": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp, vp]),
+    "bcu_index_image_size": (C.c_int, [vp, C.POINTER(C.c_uint64)]),
+    "bcu_index_export_dev": (C.c_int, [vp, vp, C.c_uint64, vp]),
+    "bcu_index_import_dev": (C.c_int, [C.c_int, vp, C.c_uint64, vp, C.POINTER(vp)]),
     "bcu_launch_count": (C.c_uint64, []),
 }
 

@@ -16,6 +16,8 @@
 // (join.cu), so results do not depend on W.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
+#include <new>
 #include <vector>
 
 #include "common.cuh"
@@ -557,6 +559,130 @@ extern "C" int bcu_index_free(bcu_index* ix) {
   DeviceGuard guard(ix->device);
   free_index_members(ix);
   delete ix;
+  return BCU_OK;
+}
+
+// ---- index image: every array of an index in ONE device blob -------------------------------------
+// so that an index built on one GPU can be shipped to the others (NCCL broadcast or a peer copy over
+// NVLink) instead of being rebuilt there. Layout: 256-byte header, then the arrays,
+// each at a 256-byte boundary. `runmax` is a build-time array and is not part of the image.
+namespace {
+constexpr uint64_t kImageMagic = 0x3158444955434942ull;  // "BICUIDX1"
+constexpr uint64_t kImageAlign = 256;
+enum { kImgLowHigh, kImgHigh, kImgId, kImgHs, kImgGroups, kImgDir, kImgDirh, kImgArrays };
+struct ImageHeader {
+  uint64_t magic, total_bytes, n, n_bins, bytes;
+  uint32_t n_groups, n_comp, class_base_len, shift, max_gval, sort_passes;
+  uint64_t offset[kImgArrays], size[kImgArrays];
+  uint8_t pad[256 - 5 * 8 - 6 * 4 - 2 * 8 * kImgArrays];
+};
+static_assert(sizeof(ImageHeader) == 256, "image header is one 256-byte block");
+
+void image_layout(const bcu_index* ix, ImageHeader* h) {
+  std::memset(h, 0, sizeof(*h));
+  h->magic = kImageMagic;
+  h->n = ix->n; h->n_bins = ix->n_bins; h->bytes = ix->bytes;
+  h->n_groups = ix->n_groups; h->n_comp = ix->n_comp; h->class_base_len = ix->class_base_len;
+  h->shift = ix->shift; h->max_gval = ix->max_gval; h->sort_passes = ix->sort_passes;
+  const uint64_t rows = ix->n ? ix->n + 4 : 0;  // the padded row arrays travel with their padding
+  h->size[kImgLowHigh] = rows * sizeof(uint2);
+  h->size[kImgHigh] = h->size[kImgId] = h->size[kImgHs] = rows * 4;
+  h->size[kImgGroups] = ix->n ? (uint64_t)ix->n_comp * ix->n_groups * sizeof(GroupDesc) : 0;
+  h->size[kImgDir] = ix->n_bins * sizeof(DirEntry);
+  h->size[kImgDirh] = ix->n_bins * 4;
+  uint64_t at = sizeof(ImageHeader);
+  for (int k = 0; k < kImgArrays; ++k) {
+    h->offset[k] = at;
+    at += (h->size[k] + kImageAlign - 1) / kImageAlign * kImageAlign;
+  }
+  h->total_bytes = at;
+}
+void** image_slots(bcu_index* ix, void** slot) {
+  slot[kImgLowHigh] = &ix->d_lowhigh; slot[kImgHigh] = &ix->d_high; slot[kImgId] = &ix->d_id;
+  slot[kImgHs] = &ix->d_hs; slot[kImgGroups] = &ix->d_groups; slot[kImgDir] = &ix->d_dir;
+  slot[kImgDirh] = &ix->d_dirh;
+  return slot;
+}
+}  // namespace
+
+extern "C" int bcu_index_image_size(const bcu_index* ix, uint64_t* bytes) {
+  if (!ix || !bytes) { set_error("bcu_index_image_size: NULL argument"); return BCU_E_INVALID; }
+  ImageHeader h;
+  image_layout(ix, &h);
+  *bytes = h.total_bytes;
+  return BCU_OK;
+}
+
+extern "C" int bcu_index_export_dev(const bcu_index* ix, void* d_image, uint64_t bytes, void* stream_) {
+  if (!ix || !d_image) { set_error("bcu_index_export_dev: NULL argument"); return BCU_E_INVALID; }
+  ImageHeader h;
+  image_layout(ix, &h);
+  if (bytes < h.total_bytes) {
+    set_error("bcu_index_export_dev: image buffer of %llu bytes, %llu needed", (unsigned long long)bytes,
+              (unsigned long long)h.total_bytes);
+    return BCU_E_CAPACITY;
+  }
+  DeviceGuard guard(ix->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  void* slot[kImgArrays];
+  image_slots(const_cast<bcu_index*>(ix), slot);
+  char* img = static_cast<char*>(d_image);
+  BCU_CUDA(cudaMemcpyAsync(img, &h, sizeof(h), cudaMemcpyHostToDevice, stream));
+  for (int k = 0; k < kImgArrays; ++k)
+    if (h.size[k])
+      BCU_CUDA(cudaMemcpyAsync(img + h.offset[k], *static_cast<void**>(slot[k]), h.size[k],
+                               cudaMemcpyDeviceToDevice, stream));
+  BCU_CUDA(cudaStreamSynchronize(stream));  // the header is a stack temporary
+  return BCU_OK;
+}
+
+extern "C" int bcu_index_import_dev(int device, const void* d_image, uint64_t bytes, void* stream_,
+                                    bcu_index** out) {
+  if (!out) { set_error("bcu_index_import_dev: out is NULL"); return BCU_E_INVALID; }
+  *out = nullptr;
+  if (!d_image || bytes < sizeof(ImageHeader)) { set_error("bcu_index_import_dev: no image"); return BCU_E_INVALID; }
+  DeviceGuard guard(device);
+  if (!guard.ok) { set_error("bcu_index_import_dev: cannot select CUDA device %d", device); return BCU_E_CUDA; }
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ImageHeader h;
+  BCU_CUDA(cudaMemcpyAsync(&h, d_image, sizeof(h), cudaMemcpyDeviceToHost, stream));
+  BCU_CUDA(cudaStreamSynchronize(stream));
+  bcu_index probe;  // recompute the layout from the header's scalars: the offsets must agree
+  probe.n = h.n; probe.n_bins = h.n_bins; probe.n_groups = h.n_groups; probe.n_comp = h.n_comp;
+  ImageHeader want;
+  image_layout(&probe, &want);
+  if (h.magic != kImageMagic || h.total_bytes != want.total_bytes || bytes < h.total_bytes ||
+      std::memcmp(h.offset, want.offset, sizeof(h.offset)) || std::memcmp(h.size, want.size, sizeof(h.size)) ||
+      h.n > 0x7fffffffull || (h.n_comp != 1 && h.n_comp != 2 && h.n_comp != 4)) {
+    set_error("bcu_index_import_dev: not an index image (or truncated)");
+    return BCU_E_INVALID;
+  }
+  bcu_index* ix = new (std::nothrow) bcu_index();
+  if (!ix) { set_error("out of host memory"); return BCU_E_NOMEM; }
+  ix->device = device;
+  ix->n = h.n; ix->n_bins = h.n_bins; ix->bytes = h.bytes;
+  ix->n_groups = h.n_groups; ix->n_comp = h.n_comp; ix->class_base_len = h.class_base_len;
+  ix->shift = h.shift; ix->max_gval = h.max_gval; ix->sort_passes = h.sort_passes;
+  keep_pool_warm(device);
+  void* slot[kImgArrays];
+  image_slots(ix, slot);
+  const char* img = static_cast<const char*>(d_image);
+  int rc = BCU_OK;
+  for (int k = 0; k < kImgArrays && rc == BCU_OK; ++k) {
+    if (!h.size[k]) continue;
+    void* p = nullptr;
+    if (cudaMallocAsync(&p, h.size[k], stream) != cudaSuccess) { rc = BCU_E_NOMEM; break; }
+    *static_cast<void**>(slot[k]) = p;
+    if (cudaMemcpyAsync(p, img + h.offset[k], h.size[k], cudaMemcpyDeviceToDevice, stream) != cudaSuccess) rc = BCU_E_CUDA;
+  }
+  if (rc == BCU_OK && cudaStreamSynchronize(stream) != cudaSuccess) rc = BCU_E_CUDA;
+  if (rc != BCU_OK) {
+    set_error("bcu_index_import_dev: %s", rc == BCU_E_NOMEM ? "out of device memory" : cudaGetErrorString(cudaGetLastError()));
+    free_index_members(ix);
+    delete ix;
+    return rc;
+  }
+  *out = ix;
   return BCU_OK;
 }
 

@@ -64,6 +64,23 @@ class DeviceIndex:
         check(lib.bcu_index_build_dev(device, n, d_group or None, d_low, d_high, stream or None, C.byref(out)))
         return cls(out.value, device)
 
+    # -- index image: build once, ship to the other GPUs (bcu_index_image_size / export / import) --------
+    def image_size(self) -> int:
+        n = C.c_uint64()
+        check(_lib.load().bcu_index_image_size(self._h, C.byref(n)))
+        return n.value
+
+    def export_dev(self, d_image: int, nbytes: int, stream: int = 0) -> None:
+        """Write the index image into ``nbytes`` of device memory at ``d_image`` (on this index's device)."""
+        check(_lib.load().bcu_index_export_dev(self._h, d_image, nbytes, stream or None))
+
+    @classmethod
+    def import_dev(cls, device: int, d_image: int, nbytes: int, stream: int = 0) -> "DeviceIndex":
+        """New index on ``device`` from an image resident there (the image may be freed afterwards)."""
+        out = vp()
+        check(_lib.load().bcu_index_import_dev(device, d_image, nbytes, stream or None, C.byref(out)))
+        return cls(out.value, device)
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             _lib.load().bcu_index_free(self._h)

@@ -37,6 +37,50 @@ def exchange_totals(local_total: int, group=None) -> List[int]:
     return [int(t.item()) for t in out]
 
 
+def broadcast_blob(blob, src: int = 0, device="cpu", group=None):
+    """Ship one uint8 tensor from rank ``src`` to every rank: 8 bytes of size first, then the payload.
+    ``blob`` is only read on ``src``. ``device``: where receivers allocate ("cpu" under gloo, a CUDA device
+    under nccl -- then the payload travels GPU to GPU over NVLink/NVSwitch, never through the host)."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    size = torch.tensor([blob.numel() if rank == src else 0], dtype=torch.int64, device=device)
+    dist.broadcast(size, src, group=group)
+    if rank != src:
+        blob = torch.empty(int(size.item()), dtype=torch.uint8, device=device)
+    elif blob.dtype != torch.uint8 or not blob.is_contiguous():
+        raise ValueError("blob must be a contiguous uint8 tensor")
+    if blob.numel():
+        dist.broadcast(blob, src, group=group)
+    return blob
+
+
+def replicate_index(build_fn: Callable, device: int, src: int = 0, group=None):
+    """Build-once / broadcast: rank ``src`` builds the index (``build_fn() ->
+    DeviceIndex`` on its GPU), exports it into one device buffer (``bcu_index_export_dev``), NCCL broadcasts
+    that buffer, and every other rank imports it (``bcu_index_import_dev``) -- instead of every rank
+    sorting the same targets. Single process / no process group: just ``build_fn()``."""
+    import torch
+    import torch.distributed as dist
+    from .interval_tree import DeviceIndex
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return build_fn()
+    rank = dist.get_rank(group)
+    dev = torch.device("cuda", device)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    ix, image = None, None
+    if rank == src:
+        ix = build_fn()
+        nbytes = ix.image_size()
+        image = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ix.export_dev(image.data_ptr(), nbytes, stream)
+    image = broadcast_blob(image, src, dev, group)
+    if rank != src:
+        torch.cuda.current_stream(dev).synchronize()  # the broadcast ran on this stream / NCCL's, be explicit
+        ix = DeviceIndex.import_dev(device, image.data_ptr(), image.numel(), stream)
+    return ix
+
+
 class ShardedJoin:
     """Runs ``join_fn`` on this rank's query range.
 

@@ -153,6 +153,19 @@ int bcu_query_any_dev(const bcu_index* index, uint64_t n_q, const uint32_t* d_qg
                       const uint32_t* d_qlow, const uint32_t* d_qhigh, uint8_t* d_any,
                       void* stream);
 
+/* ---- index image (build once, broadcast over NVLink) -----------------------------
+ * The reference rebuilds its trees in every task (mapper.hpp:147-162, mapper.cpp:128-140 builds ONE tree and
+ * shares it between threads). Across GPUs the equivalent of "share" is: build on one device, export the
+ * index into one contiguous device buffer, move that buffer with any device-to-device transport (NCCL
+ * broadcast, cudaMemcpyPeer), and import it on the receiving device. Export and import synchronise `stream`.
+ * The image is position-independent, specific to this library version, and only valid between devices of
+ * the same process group (no endianness / version negotiation). */
+int bcu_index_image_size(const bcu_index* index, uint64_t* bytes);
+/* d_image: `bytes` >= bcu_index_image_size bytes on the index's device (BCU_E_CAPACITY if smaller). */
+int bcu_index_export_dev(const bcu_index* index, void* d_image, uint64_t bytes, void* stream);
+/* d_image: an exported image resident on `device`; the new index owns copies, d_image may be freed after. */
+int bcu_index_import_dev(int device, const void* d_image, uint64_t bytes, void* stream, bcu_index** out);
+
 /* Number of kernel launches this library has issued on the calling process (all threads). */
 uint64_t bcu_launch_count(void);
 

@@ -349,3 +349,44 @@ def test_fused_pair_filters(port_oracle, kind, use_strand, seed, kw):
     assert 0 < want_q.size < qid.size
     assert np.array_equal(goff, want_off) and np.array_equal(ghq, want_q)
     assert np.array_equal(canonical(goff, ght)[1], canonical(want_off, want_t)[1])
+
+
+@pytest.mark.parametrize("seed,kw", [
+    (91, dict(n_t=30000, n_q=20000, n_groups=5, dup_frac=0.05, long_frac=0.002)),   # several length classes
+    (92, dict(n_t=5000, n_q=3000, n_groups=300, inverted_frac=0.1)),                 # binary-search groups
+    (93, dict(n_t=0, n_q=100, n_groups=1)),                                          # empty index
+])
+def test_index_image_round_trip(port_oracle, seed, kw):
+    """bcu_index_export_dev -> bcu_index_import_dev (the build-once/broadcast path of SURVEY 8f.4): the
+    imported index answers exactly like the one it was exported from, also after the source is freed."""
+    import torch
+    c = random_case(seed, **kw)
+    dev = torch.device("cuda:0")
+    stream = torch.cuda.current_stream().cuda_stream
+    src = DeviceIndex.build(c["tl"], c["th"], c["tg"])
+    nbytes = src.image_size()
+    assert nbytes >= 256 and nbytes % 256 == 0
+    image = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+    with pytest.raises(RuntimeError):
+        src.export_dev(image.data_ptr(), nbytes - 1, stream)       # BCU_E_CAPACITY
+    src.export_dev(image.data_ptr(), nbytes, stream)
+    want = src.join(c["ql"], c["qh"], c["qg"])
+    info = src.info()
+    src.close()
+    moved = image.clone()                                            # what a broadcast delivers
+    del image
+    ix = DeviceIndex.import_dev(0, moved.data_ptr(), nbytes, stream)
+    del moved                                                        # the index owns copies
+    torch.cuda.synchronize()
+    assert ix.info() == info and len(ix) == c["tl"].size
+    got = ix.join(c["ql"], c["qh"], c["qg"])
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    f = port_oracle.build(c["tl"], c["th"], c["tg"])
+    want_off, want_tid = f.query_sorted_pairs(c["ql"], c["qh"], c["qg"], threads=4)
+    assert np.array_equal(got[0], want_off) and np.array_equal(canonical(got[0], got[2])[1], want_tid)
+    assert np.array_equal(ix.any(c["ql"], c["qh"], c["qg"]), np.diff(want_off) > 0)
+    garbage = torch.zeros(4096, dtype=torch.uint8, device=dev)
+    with pytest.raises(RuntimeError):
+        DeviceIndex.import_dev(0, garbage.data_ptr(), 4096, stream)  # not an image
+    ix.close()

@@ -9,7 +9,7 @@ import pytest
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from binary_b200.sharding import ShardedJoin, assemble, shard_range
+from binary_b200.sharding import ShardedJoin, assemble, broadcast_blob, replicate_index, shard_range
 from cases import canonical, random_case
 
 
@@ -68,3 +68,34 @@ def test_two_rank_sharded_join_equals_unsharded(tmp_path):
     # the 8-byte total exchange gives every rank its global offsets without moving any pairs
     assert np.array_equal(pieces[0]["global_offsets"], want_off[: pieces[0]["stop"] + 1])
     assert np.array_equal(pieces[1]["global_offsets"], want_off[pieces[1]["start"]:])
+
+
+def _blob_worker(rank, world, port, out_dir):
+    import torch
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    src = 1  # not rank 0 on purpose
+    payload = torch.arange(100_003, dtype=torch.int64).to(torch.uint8) if rank == src else None
+    got = broadcast_blob(payload, src=src, device="cpu")
+    empty = broadcast_blob(torch.empty(0, dtype=torch.uint8) if rank == src else None, src=src, device="cpu")
+    np.save(os.path.join(out_dir, f"blob{rank}.npy"), got.numpy())
+    assert empty.numel() == 0
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_broadcast_blob_ships_size_then_payload(tmp_path):
+    """Host logic of the build-once/broadcast path (replicate_index): receivers learn the size first."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_blob_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    want = (np.arange(100_003, dtype=np.int64) & 0xFF).astype(np.uint8)
+    for r in range(2):
+        assert np.array_equal(np.load(tmp_path / f"blob{r}.npy"), want)
+
+
+def test_replicate_index_without_a_process_group_just_builds():
+    marker = object()
+    assert replicate_index(lambda: marker, device=0) is marker
