@@ -118,6 +118,7 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
                 uint64_t pair_capacity, uint32_t* d_hit_query, uint32_t* d_hit_target,
                 uint64_t* d_total, uint8_t* d_any, uint32_t query_id_base, cudaStream_t stream,
                 const uint64_t* d_offset_base = nullptr,  // device u64 added to every offset (chunked joins)
-                const bcu_filter* filter = nullptr, const uint8_t* d_qstrand = nullptr);
+                const bcu_filter* filter = nullptr, const uint8_t* d_qstrand = nullptr,
+                uint64_t* total_mapped = nullptr);  // device-visible pinned host u64 that also receives the total
 
 }  // namespace bcu

@@ -5,6 +5,8 @@
 // chunk's emit kernel starts from the previous chunk's running total, which stays on the device.
 // Device staging buffers and streams are cached per host thread and device (grow-only; bcu_trim frees).
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <memory>
 #include <vector>
@@ -28,7 +30,8 @@ struct HostCtx {
   uint32_t *d_hq = nullptr, *d_ht = nullptr;
   uint64_t cap_hq = 0, cap_ht = 0;
   uint64_t* d_totals = nullptr;
-  uint64_t* h_totals = nullptr;  // pinned
+  uint64_t* h_totals = nullptr;  // pinned and mapped: the emit kernel writes each chunk's total straight into it
+  uint64_t* h_totals_dev = nullptr;  // its device-side address
   uint64_t cap_chunks = 0;
   std::vector<cudaEvent_t> ev_in, ev_run;
 
@@ -85,7 +88,8 @@ struct HostCtx {
       d_totals = h_totals = nullptr;
       cap_chunks = 0;
       BCU_CUDA(cudaMalloc((void**)&d_totals, n_chunks * 8));
-      BCU_CUDA(cudaHostAlloc((void**)&h_totals, n_chunks * 8, cudaHostAllocDefault));
+      BCU_CUDA(cudaHostAlloc((void**)&h_totals, n_chunks * 8, cudaHostAllocMapped));
+      BCU_CUDA(cudaHostGetDevicePointer((void**)&h_totals_dev, h_totals, 0));
       cap_chunks = n_chunks;
     }
     while (ev_in.size() < n_chunks) {
@@ -164,12 +168,25 @@ static int join_host(const bcu_index* ix, const bcu_filter* filter, uint64_t n_q
     step = std::max<uint64_t>(step / 1024 * 1024, 1024);
     if (bounds.back() + step < n_q) bounds.push_back(bounds.back() + step);
   }
-  while (bounds.back() + kHostChunk < n_q) bounds.push_back(bounds.back() + kHostChunk);
+  // ... and the last two are a half and a quarter: what follows the last H2D copy (its join and its
+  // D2H) is not overlapped with anything either
+  const uint64_t tail_half = std::max<uint64_t>(kHostChunk / 2 / 1024 * 1024, 1024);
+  const uint64_t tail_quarter = std::max<uint64_t>(kHostChunk / 4 / 1024 * 1024, 1024);
+  const uint64_t tail = tail_half + tail_quarter;
+  while (bounds.back() + kHostChunk + tail < n_q) bounds.push_back(bounds.back() + kHostChunk);
+  if (bounds.back() + tail < n_q) {
+    const uint64_t t0 = (n_q - tail) / 1024 * 1024;  // chunk starts stay multiples of 1024 (128-bit paths)
+    if (t0 > bounds.back()) bounds.push_back(t0);
+    bounds.push_back(t0 + tail_half);
+  }
   bounds.push_back(n_q);
   const uint64_t n_chunks = bounds.size() - 1;
   BCU_TRY(c->prepare(ix->device, n_q, pair_capacity, n_chunks, qgroup != nullptr, hit_query != nullptr,
                      qstrand != nullptr));
 
+  const bool trace = std::getenv("BCU_HOST_TRACE") != nullptr;  // dev aid: host-side timeline on stderr
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto since = [&] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count(); };
   // 1. queue every chunk's H2D copies and kernels; nothing here blocks the host
   for (uint64_t i = 0; i < n_chunks; ++i) {
     const uint64_t b = bounds[i], n = bounds[i + 1] - b;
@@ -182,9 +199,12 @@ static int join_host(const bcu_index* ix, const bcu_filter* filter, uint64_t n_q
     BCU_TRY(launch_join(ix, kModeFused, n, qgroup ? c->d_qg + b : nullptr, c->d_ql + b, c->d_qh + b,
                         c->d_off + b, pair_capacity, hit_query ? c->d_hq : nullptr, c->d_ht, c->d_totals + i, nullptr,
                         (uint32_t)b, c->s_run, i ? c->d_totals + (i - 1) : nullptr, filter,
-                        qstrand ? c->d_qs + b : nullptr));
-    BCU_CUDA(cudaMemcpyAsync(c->h_totals + i, c->d_totals + i, 8, cudaMemcpyDeviceToHost, c->s_run));
+                        qstrand ? c->d_qs + b : nullptr, c->h_totals_dev + i));
+    // (no D2H copy of the total on s_run: it would queue behind s_out's large copies in the copy engine and
+    // stall the next chunk's kernels; the kernel writes the total into mapped host memory instead)
     BCU_CUDA(cudaEventRecord(c->ev_run[i], c->s_run));
+    if (trace) fprintf(stderr, "[bcu_join] chunk %llu (%llu queries) queued at %.0f us\n", (unsigned long long)i,
+                       (unsigned long long)n, since());
   }
   // 2. as each chunk finishes, its running total tells how many pairs to bring back
   uint64_t done_pairs = 0;
@@ -192,6 +212,8 @@ static int join_host(const bcu_index* ix, const bcu_filter* filter, uint64_t n_q
     const uint64_t b = bounds[i], n = bounds[i + 1] - b;
     BCU_CUDA(cudaEventSynchronize(c->ev_run[i]));
     const uint64_t t = c->h_totals[i];
+    if (trace) fprintf(stderr, "[bcu_join] chunk %llu joined at %.0f us, running total %llu\n", (unsigned long long)i,
+                       since(), (unsigned long long)t);
     BCU_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_run[i], 0));
     const uint64_t n_off = n + (i + 1 == n_chunks ? 1 : 0);
     BCU_CUDA(cudaMemcpyAsync(offsets + b, c->d_off + b, n_off * 8, cudaMemcpyDeviceToHost, c->s_out));
@@ -207,6 +229,7 @@ static int join_host(const bcu_index* ix, const bcu_filter* filter, uint64_t n_q
     *total = t;
   }
   BCU_CUDA(cudaStreamSynchronize(c->s_out));
+  if (trace) fprintf(stderr, "[bcu_join] last byte on the host at %.0f us\n", since());
   if (*total > pair_capacity) {
     set_error("bcu_join: %llu pairs exceed pair_capacity %llu", (unsigned long long)*total,
               (unsigned long long)pair_capacity);

@@ -85,6 +85,7 @@ struct JoinArgs {
   uint32_t* st_w;       // [same] probe state: hit bitmask, or kBigFlag | hit count
   uint32_t* st_ub;      // [same] probe state of LONG ranges only: exact end row (untouched otherwise)
   uint64_t* cta_total;  // [gridDim.x] hits per chunk
+  uint64_t* total_mapped;  // optional second copy of the total, in mapped pinned host memory
   uint32_t* big_list;   // [padded n_vq] per chunk, from its first slot on: the virtual queries with LONG ranges
   uint32_t* cta_big;    // [gridDim.x] entries of the chunk's list
   const uint64_t* base_in;  // optional: offset of the batch's first pair (chunked host pipeline)
@@ -773,6 +774,7 @@ __global__ void __launch_bounds__(kJoinThreads, kEmitMinBlocks) emit_kernel(cons
     const uint64_t t = running + a.cta_total[blockIdx.x];
     a.offsets[a.n_q] = t;
     if (a.total) *a.total = t;
+    if (a.total_mapped) *a.total_mapped = t;  // pinned host memory: visible to the host once the grid is done
   }
 
   uint4 n_lb = make_uint4(0, 0, 0, 0), n_w = make_uint4(0, 0, 0, 0);  // prefetched state of the next step
@@ -1066,7 +1068,8 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
                 const uint32_t* d_qlow, const uint32_t* d_qhigh, uint64_t* d_offsets,
                 uint64_t pair_capacity, uint32_t* d_hit_query, uint32_t* d_hit_target,
                 uint64_t* d_total, uint8_t* d_any, uint32_t query_id_base, cudaStream_t stream,
-                const uint64_t* d_offset_base, const bcu_filter* filter, const uint8_t* d_qstrand) {
+                const uint64_t* d_offset_base, const bcu_filter* filter, const uint8_t* d_qstrand,
+                uint64_t* total_mapped) {
   if (n_q > 0xfffffffeull) { set_error("query batch exceeds 2^32-2 queries"); return BCU_E_LIMIT; }
   if (mode < 0 || mode > 3) { set_error("bad join mode %d", mode); return BCU_E_INVALID; }
   const bool prefix = (mode == kModeCount || mode == kModeFused);
@@ -1106,6 +1109,7 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
   a.hit_query = d_hit_query;
   a.hit_target = d_hit_target;
   a.total = d_total;
+  a.total_mapped = total_mapped;
   a.any = d_any;
   a.qid_base = query_id_base;
   a.st_lb = nullptr;
