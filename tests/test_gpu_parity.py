@@ -390,3 +390,30 @@ def test_index_image_round_trip(port_oracle, seed, kw):
     with pytest.raises(RuntimeError):
         DeviceIndex.import_dev(0, garbage.data_ptr(), 4096, stream)  # not an image
     ix.close()
+
+
+@pytest.mark.parametrize("label", ["proper", "inverted_targets_in_some_groups", "inverted_queries", "ties",
+                                   "length_classes", "point_targets"])
+def test_long_ranges_rank_count_and_its_fallbacks(port_oracle, label):
+    """Long candidate ranges are COUNTED by rank arithmetic (#low <= q.high - #high < q.low) when the
+    segment has no inverted row and the query is proper, and scanned otherwise. Both ways, and their mix
+    inside one batch, must give the reference's pairs."""
+    rng = np.random.default_rng(1234)
+    kw = dict(n_t=24000, n_q=6000, span=200000, max_len=60000, n_groups=4)   # ~hundreds of candidates / query
+    if label == "ties":
+        kw.update(span=3000, max_len=900)        # many equal lows and highs: lower_bound ties in the rank view
+    if label == "length_classes":
+        kw.update(span=3_000_000, max_len=40000, long_frac=0.01)
+    c = random_case(77, **kw)
+    if label == "inverted_targets_in_some_groups":   # groups 0 and 1 lose the shortcut, 2 and 3 keep it
+        sel = np.flatnonzero(c["tg"] < 2)
+        idx = rng.choice(sel, sel.size // 20, replace=False)
+        c["th"][idx] = c["tl"][idx] // 3
+    if label == "inverted_queries":
+        idx = rng.choice(c["ql"].size, c["ql"].size // 5, replace=False)
+        c["ql"][idx], c["qh"][idx] = c["qh"][idx].copy(), c["ql"][idx].copy()
+    if label == "point_targets":
+        c["th"] = c["tl"].copy()
+        c["qh"] = np.minimum(c["ql"].astype(np.uint64) + 30000, 0xFFFFFFFF).astype(np.uint32)
+    hits = _check_all_entry_points(c, port_oracle)
+    assert hits > 30 * c["ql"].size or label in ("inverted_queries", "length_classes", "point_targets")
