@@ -57,10 +57,10 @@ struct GroupDesc {
   uint32_t gval;
   uint32_t row_begin;
   uint32_t row_end;
-  uint32_t nb;  // number of bins = directory entries = (cmax >> shift) + 1, cmax = max coordinate in group
+  uint32_t nb;  // number of bins = directory entries = (cmax >> shift) + 1, cmax = max coordinate in the segment
   uint64_t bin_base;
   uint32_t proper;  // 1 = every row of the segment has low <= high (enables the O(1) long-range count)
-  uint32_t pad;
+  uint32_t shift;   // log2 of the bin width W of this segment's length class
 };
 
 constexpr int kMaxSmemGroups = 256;
@@ -83,7 +83,8 @@ struct bcu_index {
   uint32_t n_groups = 0;
   uint32_t n_comp = 1;          // length-class slots a query probes: 1, 2 or 4 (join.cu: virtual queries)
   uint32_t class_base_len = 0;  // class c holds lengths < class_base_len * 4^c
-  uint32_t shift = 0;
+  uint32_t shift = 0;           // bin shift of length class 0 (reported by bcu_index_get_info)
+  uint32_t shifts = 0;          // bin shift of class c in byte c: sparse classes get wider bins, i.e. small directories
   uint32_t max_gval = 0;  // largest group value (selects the direct group map in join.cu)
   uint32_t sort_passes = 0;
   uint64_t n_bins = 0;

@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kThreads)
 
 // dirh[e] = first index of the segment's slice of hs with hs >= b*W (one thread per directory entry)
 __global__ void __launch_bounds__(kThreads)
-    fill_dirh_kernel(const GroupDesc* __restrict__ groups, uint32_t n_groups, uint32_t shift,
+    fill_dirh_kernel(const GroupDesc* __restrict__ groups, uint32_t n_groups,
                      const uint32_t* __restrict__ hs, uint32_t* __restrict__ dirh, uint64_t n_bins) {
   uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_bins) return;
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kThreads)
     if (groups[mid].bin_base <= e) lo = mid; else hi = mid;
   }
   const GroupDesc g = groups[lo];
-  const uint32_t t0 = (uint32_t)((e - g.bin_base) << shift);
+  const uint32_t t0 = (uint32_t)((e - g.bin_base) << g.shift);
   uint32_t a = g.row_begin, b = g.row_end;
   while (a < b) {
     uint32_t m = a + ((b - a) >> 1);
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(kThreads)
 
 // one thread per directory entry
 __global__ void __launch_bounds__(kThreads)
-    fill_directory_kernel(const GroupDesc* __restrict__ groups, uint32_t n_groups, uint32_t shift,
+    fill_directory_kernel(const GroupDesc* __restrict__ groups, uint32_t n_groups,
                           const uint2* __restrict__ lowhigh, const uint32_t* __restrict__ runmax,
                           DirEntry* __restrict__ dir, uint64_t n_bins) {
   uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -196,8 +196,8 @@ __global__ void __launch_bounds__(kThreads)
     if (groups[mid].bin_base <= e) lo = mid; else hi = mid;
   }
   const GroupDesc g = groups[lo];
-  const uint64_t t0 = (e - g.bin_base) << shift;  // b * W       (<= cmax, fits 32 bits)
-  const uint64_t t1 = t0 + (1ull << shift);       // (b + 1) * W (may exceed 32 bits in the last bin)
+  const uint64_t t0 = (e - g.bin_base) << g.shift;  // b * W       (<= cmax, fits 32 bits)
+  const uint64_t t1 = t0 + (1ull << g.shift);       // (b + 1) * W (may exceed 32 bits in the last bin)
   uint32_t a = g.row_begin, b = g.row_end;
   while (a < b) {  // first row with runmax >= b*W
     uint32_t m = a + ((b - a) >> 1);
@@ -442,23 +442,36 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
     BCU_LAUNCHED();
   }
 
-  // ---- bin width: smallest shift whose directory stays within ~bin_factor entries per target ----
+  // ---- bin width, per length class: the smallest shift whose directory stays within ~bin_factor entries
+  // per row OF THAT CLASS. A sparse class (the few long intervals) thus gets wide bins and a directory small
+  // enough to stay in L2, instead of one as large as the dense class's (bins follow coordinates, not rows).
   const double factor = env_double("BCU_BIN_FACTOR", 2.0);
-  const uint64_t budget = std::max<uint64_t>((uint64_t)(factor * (double)n), 1024) + 2ull * n_segs;
-  uint32_t shift = 0;
-  uint64_t n_bins = 0;
-  for (shift = 0; shift <= 31; ++shift) {
-    n_bins = 0;
-    for (uint32_t g = 0; g < n_segs; ++g) n_bins += ((uint64_t)cmax[g] >> shift) + 1;
-    if (n_bins <= budget) break;
+  uint32_t class_shift[4] = {0, 0, 0, 0};
+  for (uint32_t c = 0; c < n_comp; ++c) {
+    uint64_t rows_c = 0, segs_c = 0;
+    for (uint32_t s = 0; s < n_segs; ++s)
+      if ((uint32_t)(seg[s] >> 32) == c) {
+        rows_c += ((s + 1 < n_segs) ? heads[s + 1] : (uint32_t)n) - heads[s];
+        ++segs_c;
+      }
+    const uint64_t budget = std::max<uint64_t>((uint64_t)(factor * (double)rows_c), 1024) + 2ull * segs_c;
+    uint32_t sh = 0;
+    for (sh = 0; sh < 31; ++sh) {
+      uint64_t bins = 0;
+      for (uint32_t s = 0; s < n_segs; ++s)
+        if ((uint32_t)(seg[s] >> 32) == c) bins += ((uint64_t)cmax[s] >> sh) + 1;
+      if (bins <= budget) break;
+    }
+    class_shift[c] = sh;
   }
-  if (shift > 31) shift = 31;
+  const uint32_t shift = class_shift[0];
+  uint64_t n_bins = 0;
   // compact list of the segments that exist (directory fill) + the query-side table [component][group]
   std::vector<GroupDesc> segs(n_segs), table((size_t)n_comp * n_groups);
   for (uint32_t c = 0; c < n_comp; ++c)
     for (uint32_t g = 0; g < n_groups; ++g) {
       GroupDesc& d = table[(size_t)c * n_groups + g];
-      d.gval = gval[g]; d.row_begin = d.row_end = 0; d.nb = 0; d.bin_base = 0; d.proper = 0; d.pad = 0;
+      d.gval = gval[g]; d.row_begin = d.row_end = 0; d.nb = 0; d.bin_base = 0; d.proper = 0; d.shift = class_shift[c];
     }
   n_bins = 0;
   for (uint32_t s = 0; s < n_segs; ++s) {
@@ -466,12 +479,12 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
     d.gval = (uint32_t)seg[s];
     d.row_begin = heads[s];
     d.row_end = (s + 1 < n_segs) ? heads[s + 1] : (uint32_t)n;
-    d.nb = (uint32_t)(((uint64_t)cmax[s] >> shift) + 1);
+    const uint32_t comp = (uint32_t)(seg[s] >> 32);
+    d.shift = class_shift[comp];
+    d.nb = (uint32_t)(((uint64_t)cmax[s] >> d.shift) + 1);
     d.bin_base = n_bins;
     d.proper = proper[s] ? 1u : 0u;
-    d.pad = 0;
     n_bins += (uint64_t)d.nb;
-    const uint32_t comp = (uint32_t)(seg[s] >> 32);
     const uint32_t g = (uint32_t)(std::lower_bound(gval.begin(), gval.end(), d.gval) - gval.begin());
     table[(size_t)comp * n_groups + g] = d;
   }
@@ -480,6 +493,7 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
   ix->class_base_len = base_len;
   ix->max_gval = n_groups ? gval[n_groups - 1] : 0;
   ix->shift = shift;
+  ix->shifts = class_shift[0] | (class_shift[1] << 8) | (class_shift[2] << 16) | (class_shift[3] << 24);
   ix->n_bins = n_bins;
   GroupDesc* d_segs;
   BCU_CUDA(tmp.alloc(&d_segs, n_segs));
@@ -490,12 +504,12 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
   BCU_CUDA(cudaMemcpyAsync(ix->d_groups, table.data(), table.size() * sizeof(GroupDesc),
                            cudaMemcpyHostToDevice, stream));
   fill_directory_kernel<<<(unsigned)((n_bins + kThreads - 1) / kThreads), kThreads, 0, stream>>>(
-      d_segs, n_segs, shift, ix->d_lowhigh, ix->d_runmax, ix->d_dir, n_bins);
+      d_segs, n_segs, ix->d_lowhigh, ix->d_runmax, ix->d_dir, n_bins);
   BCU_LAUNCHED();
   BCU_CUDA(cudaMallocAsync((void**)&ix->d_dirh, n_bins * 4, stream));
   ix->bytes += n_bins * 4;
   fill_dirh_kernel<<<(unsigned)((n_bins + kThreads - 1) / kThreads), kThreads, 0, stream>>>(
-      d_segs, n_segs, shift, ix->d_hs, ix->d_dirh, n_bins);
+      d_segs, n_segs, ix->d_hs, ix->d_dirh, n_bins);
   BCU_LAUNCHED();
   BCU_CUDA(cudaStreamSynchronize(stream));  // host vectors are temporaries
   return BCU_OK;
@@ -567,14 +581,14 @@ extern "C" int bcu_index_free(bcu_index* ix) {
 // NVLink) instead of being rebuilt there. Layout: 256-byte header, then the arrays,
 // each at a 256-byte boundary. `runmax` is a build-time array and is not part of the image.
 namespace {
-constexpr uint64_t kImageMagic = 0x3158444955434942ull;  // "BICUIDX1"
+constexpr uint64_t kImageMagic = 0x3258444955434942ull;  // "BICUIDX2"
 constexpr uint64_t kImageAlign = 256;
 enum { kImgLowHigh, kImgHigh, kImgId, kImgHs, kImgGroups, kImgDir, kImgDirh, kImgArrays };
 struct ImageHeader {
   uint64_t magic, total_bytes, n, n_bins, bytes;
-  uint32_t n_groups, n_comp, class_base_len, shift, max_gval, sort_passes;
+  uint32_t n_groups, n_comp, class_base_len, shift, max_gval, sort_passes, shifts, reserved;
   uint64_t offset[kImgArrays], size[kImgArrays];
-  uint8_t pad[256 - 5 * 8 - 6 * 4 - 2 * 8 * kImgArrays];
+  uint8_t pad[256 - 5 * 8 - 8 * 4 - 2 * 8 * kImgArrays];
 };
 static_assert(sizeof(ImageHeader) == 256, "image header is one 256-byte block");
 
@@ -583,7 +597,7 @@ void image_layout(const bcu_index* ix, ImageHeader* h) {
   h->magic = kImageMagic;
   h->n = ix->n; h->n_bins = ix->n_bins; h->bytes = ix->bytes;
   h->n_groups = ix->n_groups; h->n_comp = ix->n_comp; h->class_base_len = ix->class_base_len;
-  h->shift = ix->shift; h->max_gval = ix->max_gval; h->sort_passes = ix->sort_passes;
+  h->shift = ix->shift; h->max_gval = ix->max_gval; h->sort_passes = ix->sort_passes; h->shifts = ix->shifts;
   const uint64_t rows = ix->n ? ix->n + 4 : 0;  // the padded row arrays travel with their padding
   h->size[kImgLowHigh] = rows * sizeof(uint2);
   h->size[kImgHigh] = h->size[kImgId] = h->size[kImgHs] = rows * 4;
@@ -662,7 +676,7 @@ extern "C" int bcu_index_import_dev(int device, const void* d_image, uint64_t by
   ix->device = device;
   ix->n = h.n; ix->n_bins = h.n_bins; ix->bytes = h.bytes;
   ix->n_groups = h.n_groups; ix->n_comp = h.n_comp; ix->class_base_len = h.class_base_len;
-  ix->shift = h.shift; ix->max_gval = h.max_gval; ix->sort_passes = h.sort_passes;
+  ix->shift = h.shift; ix->max_gval = h.max_gval; ix->sort_passes = h.sort_passes; ix->shifts = h.shifts;
   keep_pool_warm(device);
   void* slot[kImgArrays];
   image_slots(ix, slot);

@@ -63,7 +63,7 @@ struct JoinArgs {
   const uint32_t* __restrict__ dirh;  // per directory entry: first index of hs with value >= b*W
   const GroupDesc* __restrict__ groups;
   uint32_t n_groups;
-  uint32_t shift;
+  uint32_t shifts;  // bin shift of length-class slot c in byte c
   uint32_t max_gval;
   const uint32_t* __restrict__ qgroup;
   const uint32_t* __restrict__ qlow;
@@ -207,12 +207,19 @@ __device__ __forceinline__ void load_queries(const JoinArgs& a, uint32_t v0, uin
   }
 }
 
+// Bin shift of a length-class slot. Virtual query v = q * n_comp + slot and every lane starts a step at a
+// multiple of kQPT >= n_comp, so the slot (hence the shift) of a lane's j-th query is j & (n_comp - 1):
+// warp-uniform and loop-invariant, the callers compute the four shifts once.
+__device__ __forceinline__ uint32_t slot_shift(const JoinArgs& a, uint32_t slot) {
+  return (a.shifts >> (8u * slot)) & 31u;
+}
+
 // K3 step 1: candidate row range [lb, lb+len) of one query. `valid` = the query exists.
 template <bool FILT>
 __device__ __forceinline__ void query_bounds(const JoinArgs& a, const GroupTables& tb, bool valid,
-                                             uint32_t slot, uint32_t ql, uint32_t qh, uint32_t qg,
-                                             uint32_t strand, uint32_t& lb, uint32_t& len,
-                                             uint32_t& inline_mask) {
+                                             uint32_t slot, uint32_t shift, uint32_t ql, uint32_t qh,
+                                             uint32_t qg, uint32_t strand, uint32_t& lb, uint32_t& len,
+                                             uint32_t& inline_mask) {  // shift = slot_shift(a, slot)
   const bool in_smem = a.n_groups * a.n_comp <= (uint32_t)kMaxSmemGroups;
   const bool direct = in_smem && a.max_gval < (uint32_t)kDirectGroups;
   lb = 0;
@@ -248,9 +255,9 @@ __device__ __forceinline__ void query_bounds(const JoinArgs& a, const GroupTable
       }
     }
   }
-  const uint32_t b_lo = ql >> a.shift;
+  const uint32_t b_lo = ql >> shift;
   if (b_lo < nb) {  // otherwise unknown group, or q.low lies beyond every high of the group
-    uint32_t b_hi = qh >> a.shift;
+    uint32_t b_hi = qh >> shift;
     if (b_hi >= nb) b_hi = nb - 1u;
     // {lb(b_lo), ub(b_lo + 1), row lb}: all a one-bin query with one candidate needs
     const uint4 e = ldg_u4(reinterpret_cast<const uint4*>(a.dir + bin_base + b_lo));
@@ -361,7 +368,7 @@ __device__ __forceinline__ uint32_t count_by_ranks(const JoinArgs& a, const Grou
   if (!proper) return kNoRank;
   const uint64_t bin_base = in_smem ? tb.g_base[gi] : a.groups[gi].bin_base;
   const uint32_t row_end = in_smem ? tb.g_re[gi] : a.groups[gi].row_end;
-  uint32_t i = a.dirh[bin_base + (ql >> a.shift)];  // b_lo < nb: the range is non-empty
+  uint32_t i = a.dirh[bin_base + (ql >> slot_shift(a, slot))];  // b_lo < nb: the range is non-empty
   while (i < row_end && a.hs[i] < ql) ++i;
   return ub_exact > i ? ub_exact - i : 0u;
 }
@@ -630,6 +637,8 @@ __global__ void __launch_bounds__(kJoinThreads, kProbeMinBlocks) probe_kernel(co
   const uint64_t chunk_end = min(chunk_begin + (uint64_t)a.chunk, (uint64_t)a.n_vq);
   uint32_t* const list = a.big_list + chunk_begin;
   uint64_t acc = 0;  // hits of this lane's queries over the whole chunk (short ranges)
+  const uint32_t shift_of[kQPT] = {slot_shift(a, 0), slot_shift(a, 1u & (a.n_comp - 1u)),
+                                   slot_shift(a, 2u & (a.n_comp - 1u)), slot_shift(a, 3u & (a.n_comp - 1u))};
 
   uint64_t w0 = chunk_begin + (uint64_t)warp * kWarpTile;
   uint32_t nql[kQPT], nqh[kQPT], nqg[kQPT];  // prefetched queries of the next step
@@ -646,7 +655,7 @@ __global__ void __launch_bounds__(kJoinThreads, kProbeMinBlocks) probe_kernel(co
     for (int j = 0; j < kQPT; ++j) {
       strand[j] = 0;
       if (FILT && a.qstrand && q0 + j < a.n_vq) strand[j] = a.qstrand[(q0 + j) >> a.comp_shift];
-      query_bounds<FILT>(a, tb, q0 + j < a.n_vq, (q0 + j) & (a.n_comp - 1u), ql[j], qh[j], qg[j], strand[j], lb[j],
+      query_bounds<FILT>(a, tb, q0 + j < a.n_vq, j & (a.n_comp - 1u), shift_of[j], ql[j], qh[j], qg[j], strand[j], lb[j],
                          len[j], w[j]);
     }
     scan_short<FILT>(a, ql, qh, strand, lb, len, w);
@@ -965,6 +974,8 @@ __global__ void __launch_bounds__(kJoinThreads, kJoinMinBlocks) direct_kernel(co
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   load_group_tables(a, tb);
   const uint32_t n_tiles = (uint32_t)(((uint64_t)a.n_vq + kCtaTile - 1) / kCtaTile);
+  const uint32_t shift_of[kQPT] = {slot_shift(a, 0), slot_shift(a, 1u & (a.n_comp - 1u)),
+                                   slot_shift(a, 2u & (a.n_comp - 1u)), slot_shift(a, 3u & (a.n_comp - 1u))};
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint32_t w0 = tile * (uint32_t)kCtaTile + (uint32_t)warp * kWarpTile;
     const uint32_t q0 = w0 + (uint32_t)lane * kQPT;
@@ -974,7 +985,7 @@ __global__ void __launch_bounds__(kJoinThreads, kJoinMinBlocks) direct_kernel(co
     const uint32_t no_strand[kQPT] = {0, 0, 0, 0};
 #pragma unroll
     for (int j = 0; j < kQPT; ++j)
-      query_bounds<false>(a, tb, q0 + j < a.n_vq, (q0 + j) & (a.n_comp - 1u), ql[j], qh[j], qg[j], 0u, lb[j], len[j],
+      query_bounds<false>(a, tb, q0 + j < a.n_vq, j & (a.n_comp - 1u), shift_of[j], ql[j], qh[j], qg[j], 0u, lb[j], len[j],
                           mask[j]);
     scan_short<false>(a, ql, qh, no_strand, lb, len, mask);
     bool big[kQPT];
@@ -1090,7 +1101,7 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
   a.dirh = ix->d_dirh;
   a.groups = ix->d_groups;
   a.n_groups = ix->n_groups;
-  a.shift = ix->shift;
+  a.shifts = ix->shifts;
   a.max_gval = ix->max_gval;
   a.qgroup = d_qgroup;
   a.qlow = d_qlow;
@@ -1146,6 +1157,11 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
   void* scratch = nullptr;
   const uint64_t grid_even = ((uint64_t)grid + 1) & ~1ull;  // keeps the state arrays 16-byte aligned
   BCU_CUDA(cudaMallocAsync(&scratch, padded * 16 + grid_even * 12, stream));
+  struct ScratchGuard {  // stream-ordered free on every exit path
+    void* p;
+    cudaStream_t s;
+    ~ScratchGuard() { cudaFreeAsync(p, s); }
+  } scratch_guard{scratch, stream};
   a.cta_total = reinterpret_cast<uint64_t*>(scratch);
   a.st_lb = reinterpret_cast<uint32_t*>(a.cta_total + grid_even);
   a.st_w = a.st_lb + padded;
@@ -1164,7 +1180,6 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
   } else {
     BCU_TRY(launch_dependent(emit_kernel<false, false>, grid, stream, a));
   }
-  BCU_CUDA(cudaFreeAsync(scratch, stream));
   return BCU_OK;
 }
 
