@@ -88,6 +88,7 @@ struct JoinArgs {
   uint64_t* total_mapped;  // optional second copy of the total, in mapped pinned host memory
   uint32_t* big_list;   // [padded n_vq] per chunk, from its first slot on: the virtual queries with LONG ranges
   uint32_t* cta_big;    // [gridDim.x] entries of the chunk's list
+  uint32_t long_split;  // K4b: CTAs per chunk list
   const uint64_t* base_in;  // optional: offset of the batch's first pair (chunked host pipeline)
   // optional pair filter applied ON TOP of the overlap predicate (sv2nl's check_condition, fused)
   uint32_t filter_kind;     // bcu_filter_kind
@@ -929,12 +930,14 @@ __global__ void __launch_bounds__(kJoinThreads, kEmitMinBlocks) emit_kernel(cons
 constexpr int kLongMinBlocks = BCU_LONG_MB;
 __global__ void __launch_bounds__(kJoinThreads, kLongMinBlocks) emit_long_kernel(const JoinArgs a) {
   grid_dependency_wait();  // K4's offsets (and through it K3's lists)
-  const uint32_t n_list = a.cta_big[blockIdx.x];
+  // a.long_split CTAs share one chunk's list (this kernel runs more CTAs per SM than K3, whose grid made the lists)
+  const uint32_t chunk_id = blockIdx.x / a.long_split, part = blockIdx.x % a.long_split;
+  const uint32_t n_list = a.cta_big[chunk_id];
   if (n_list == 0) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t* const list = a.big_list + (uint64_t)blockIdx.x * a.chunk;
+  const uint32_t* const list = a.big_list + (uint64_t)chunk_id * a.chunk;
   const LongCtx c = long_ctx(a);
-  for (uint32_t i0 = warp * 32; i0 < n_list; i0 += kJoinThreads) {  // warp-uniform trip count
+  for (uint32_t i0 = (part * kJoinWarps + warp) * 32; i0 < n_list; i0 += kJoinThreads * a.long_split) {  // warp-uniform
     const bool have = i0 + lane < n_list;
     LongRange mine;
     mine.lb = mine.ub = mine.ql = mine.qh = mine.strand = mine.cnt = mine.qid = 0;
@@ -1148,6 +1151,7 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
   a.cta_total = nullptr;
   a.big_list = nullptr;
   a.cta_big = nullptr;
+  a.long_split = 1;
   a.base_in = d_offset_base;
   const bool filt = filter && filter->kind != BCU_FILTER_NONE;
   a.filter_kind = filt ? filter->kind : 0u;
@@ -1160,7 +1164,15 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
     return BCU_E_INVALID;
   }
   const uint64_t n_tiles = (n_vq + kCtaTile - 1) / kCtaTile;
-  const uint64_t cta_budget = (uint64_t)sm_count(ix->device) * kJoinMinBlocks * 2;  // two waves of CTAs
+  // One wave: every CTA of the grid is resident from the start (4 per SM for K3/K4). Measured on B with
+  // 1/2/3/4/6 waves: 191/203/198/207/205 us -- a second wave starts staggered behind the first one's
+  // stragglers and the per-CTA prologues repeat. BCU_WAVES overrides (finer chunks balance skewed batches).
+  static const uint64_t waves = [] {
+    const char* e = getenv("BCU_WAVES");
+    const long v = e ? atol(e) : 1;
+    return (uint64_t)(v < 1 ? 1 : v);
+  }();
+  const uint64_t cta_budget = (uint64_t)sm_count(ix->device) * kJoinMinBlocks * waves;
   if (!prefix) {
     const unsigned grid = (unsigned)(n_tiles < cta_budget ? n_tiles : cta_budget);
     if (mode == kModeScatter) direct_kernel<kModeScatter><<<grid, kJoinThreads, 0, stream>>>(a);
@@ -1195,7 +1207,11 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
   if (mode == kModeFused) {
     if (filt) BCU_TRY(launch_dependent(emit_kernel<true, true>, grid, stream, a));
     else BCU_TRY(launch_dependent(emit_kernel<true, false>, grid, stream, a));
-    if (!filt) BCU_TRY(launch_dependent(emit_long_kernel, grid, stream, a));
+    if (!filt) {  // about two waves of K4b's own occupancy
+      a.long_split = (uint32_t)std::min<uint64_t>(
+          8, std::max<uint64_t>(1, ((uint64_t)sm_count(ix->device) * kLongMinBlocks * 2 + grid - 1) / grid));
+      BCU_TRY(launch_dependent(emit_long_kernel, grid * a.long_split, stream, a));
+    }
   } else {
     BCU_TRY(launch_dependent(emit_kernel<false, false>, grid, stream, a));
   }
