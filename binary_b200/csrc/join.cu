@@ -1208,8 +1208,9 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
     if (filt) BCU_TRY(launch_dependent(emit_kernel<true, true>, grid, stream, a));
     else BCU_TRY(launch_dependent(emit_kernel<true, false>, grid, stream, a));
     if (!filt) {  // about two waves of K4b's own occupancy
+      static const uint64_t long_waves = [] { const char* e = getenv("BCU_LONG_WAVES"); long v = e ? atol(e) : 2; return (uint64_t)(v < 1 ? 1 : v); }();
       a.long_split = (uint32_t)std::min<uint64_t>(
-          8, std::max<uint64_t>(1, ((uint64_t)sm_count(ix->device) * kLongMinBlocks * 2 + grid - 1) / grid));
+          16, std::max<uint64_t>(1, ((uint64_t)sm_count(ix->device) * kLongMinBlocks * long_waves + grid - 1) / grid));
       BCU_TRY(launch_dependent(emit_long_kernel, grid * a.long_split, stream, a));
     }
   } else {
