@@ -15,6 +15,8 @@
 // candidate row along; the few rows of slack it admits are rejected by the exact predicate in the scan
 // (join.cu), so results do not depend on W.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -317,6 +319,14 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
   ix->n = n;
   keep_pool_warm(ix->device);
   if (n == 0) return BCU_OK;
+  const bool trace = std::getenv("BCU_BUILD_TRACE") != nullptr;  // dev aid: phase timeline on stderr (adds syncs)
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what) {
+    if (!trace) return;
+    cudaStreamSynchronize(stream);
+    fprintf(stderr, "[bcu_index_build] %-28s %8.0f us\n", what,
+            std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count());
+  };
   TempBuffers tmp(stream);
   uint64_t *keys_a, *keys_b, *segkey;
   uint32_t *vals_a, *vals_b, *head_rows, *counters;
@@ -330,6 +340,7 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
                                       // [6..7] sum of lengths (u64)
   BCU_CUDA(cudaMemsetAsync(counters, 0, 32, stream));
 
+  mark("temporaries allocated");
   // ---- K1: sort by (group, low) --------------------------------------------------------------------
   const unsigned grid_n = (unsigned)std::min<uint64_t>((n + kThreads - 1) / kThreads, 148ull * 16);
   make_keys_kernel<<<grid_n, kThreads, 0, stream>>>(d_group, d_low, n, keys_a, vals_a,
@@ -343,6 +354,7 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
   BCU_TRY(radix_sort_pairs(keys_a, keys_b, vals_a, vals_b, n, varying, stream, &keys, &vals,
                            &ix->sort_passes));
 
+  mark("K1 sort");
   // ---- K2: rows, running max, segments ---------------------------------------------------------------
   BCU_TRY(alloc_rows(ix, n, stream));
   BCU_CUDA(cudaMallocAsync((void**)&ix->d_runmax, n * 4, stream));
@@ -362,6 +374,7 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
   uint64_t span = 0;
   for (uint32_t g = 0; g < n_groups; ++g) { gval[g] = (uint32_t)seg[g]; span += (uint64_t)cmax[g] + 1; }
 
+  mark("rows, running max, segments");
   // ---- length classes (AIList-style decomposition) -------------------------------------------------
   // A target much longer than its neighbours drags the running max along and with it the first candidate
   // row of every later query. Targets are therefore split by length into up to 4 classes, each a 4x band
@@ -414,6 +427,7 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
   }
   const uint32_t n_segs = (uint32_t)heads.size();
 
+  mark("length classes");
   // ---- second sorted view: each segment's `high` values ascending + "all rows proper" flags ----------
   // With every row proper (low <= high) and a proper query, {rows with high < q.low} is a subset of
   // {rows with low <= q.high}, so a range's hit count is a difference of two ranks and long ranges
@@ -442,6 +456,7 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
     BCU_LAUNCHED();
   }
 
+  mark("rank view (second sort)");
   // ---- bin width, per length class: the smallest shift whose directory stays within ~bin_factor entries
   // per row OF THAT CLASS. A sparse class (the few long intervals) thus gets wide bins and a directory small
   // enough to stay in L2, instead of one as large as the dense class's (bins follow coordinates, not rows).
@@ -512,6 +527,7 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
       d_segs, n_segs, ix->d_hs, ix->d_dirh, n_bins);
   BCU_LAUNCHED();
   BCU_CUDA(cudaStreamSynchronize(stream));  // host vectors are temporaries
+  mark("directories");
   return BCU_OK;
 }
 
