@@ -17,6 +17,8 @@
 
 #include <algorithm>
 #include <array>
+#include <chrono>
+#include <cstdio>
 #include <cstdint>
 #include <map>
 #include <string>
@@ -46,28 +48,44 @@ struct Names {  // id <-> string tables shared by both files
   std::vector<std::string> chroms;  // sorted: id order == lexicographic order
   std::vector<std::string> types;
   std::unordered_map<std::string, std::uint32_t> chrom_id, type_id;
-  void build(const VcfTable& a, const VcfTable& b) {
-    for (const VcfTable* t : {&a, &b}) {
+  // per-file dictionary id (vcf_text.hpp interns while parsing) -> shared id; index 0 = NL file, 1 = SV file
+  std::array<std::vector<std::uint32_t>, 2> chrom_of, type_of;
+  std::uint32_t no_chrom = 0;  // what a record without CHR2 gets: the smallest id, never used
+  void build(const VcfTable& nl, const VcfTable& sv) {
+    const VcfTable* tables[2] = {&nl, &sv};
+    chrom_id.emplace("", 0);  // the reference's default-constructed chr2 (empty string sorts first)
+    for (const VcfTable* t : tables) {
       for (auto const& c : t->contigs) chrom_id.emplace(c, 0);
-      for (auto const& c : t->chrom) chrom_id.emplace(c, 0);
-      for (auto const& c : t->chr2) chrom_id.emplace(c, 0);
-      for (auto const& c : t->svtype) type_id.emplace(c, 0);
+      for (auto const& c : t->chrom_names) chrom_id.emplace(c, 0);
+      for (auto const& c : t->type_names) type_id.emplace(c, 0);
     }
     for (auto const& kv : chrom_id) chroms.push_back(kv.first);
     std::sort(chroms.begin(), chroms.end());
     for (std::uint32_t i = 0; i < chroms.size(); ++i) chrom_id[chroms[i]] = i;
     for (auto& kv : type_id) { kv.second = (std::uint32_t)types.size(); types.push_back(kv.first); }
+    no_chrom = chrom_id.at("");
+    for (int f = 0; f < 2; ++f) {
+      for (auto const& c : tables[f]->chrom_names) chrom_of[f].push_back(chrom_id.at(c));
+      for (auto const& c : tables[f]->type_names) type_of[f].push_back(type_id.at(c));
+    }
+  }
+  [[nodiscard]] std::uint32_t type_or_none(const std::string& name) const {  // shared id of an SVTYPE, or ~0
+    auto it = type_id.find(name);
+    return it == type_id.end() ? 0xffffffffu : it->second;
   }
 };
 
-inline Rec record_at(const VcfTable& t, const Names& names, std::size_t i) {
+// file: 0 = the NL table, 1 = the SV table (selects the id translation)
+inline Rec record_at(const VcfTable& t, const Names& names, int file, std::size_t i, std::uint32_t tra_type,
+                     std::uint32_t bnd_type) {
   Rec r;
-  r.chrom = names.chrom_id.at(t.chrom[i]);
-  r.chr2 = names.chrom_id.at(t.chr2[i]);  // "" for non-TRA/BND records: a valid (smallest) id, never used
+  r.chrom = names.chrom_of[file][t.chrom[i]];
+  r.chr2 = t.chr2[i] == kNoChrom ? names.no_chrom : names.chrom_of[file][t.chr2[i]];
   r.pos = t.pos[i];
   r.svend = t.svend[i];
-  r.type = (std::uint8_t)names.type_id.at(t.svtype[i]);
-  r.two_chrom = t.svtype[i] == "TRA" || t.svtype[i] == "BND";
+  const std::uint32_t type = names.type_of[file][t.svtype[i]];
+  r.type = (std::uint8_t)type;
+  r.two_chrom = type == tra_type || type == bnd_type;
   r.strand1 = t.strand1[i] != 0;
   r.strand2 = t.strand2[i] != 0;
   return r;
@@ -156,6 +174,7 @@ struct Options {
   std::uint32_t diff = 1000000;  // --dis default, main.cpp:91
   bool use_strand = true;
   int device = 0;
+  bool debug = false;  // per-mapper phase times on stderr
 };
 
 struct Sv2nlOutput { std::vector<std::string> dup, inv, tra; };
@@ -188,10 +207,25 @@ std::vector<std::string> emit_lines(const Names& names, const std::vector<Rec>& 
 inline Sv2nlOutput map_sv2nl(const VcfTable& nl, const VcfTable& sv, const Options& opt) {
   Sv2nlOutput out;
   Names names;
+  auto clock = [] { return std::chrono::steady_clock::now(); };
+  auto t_last = clock();
+  auto lap = [&](const char* what) {
+    if (!opt.debug) return;
+    const auto t = clock();
+    std::fprintf(stderr, "  [map] %-22s %.3f s\n", what, std::chrono::duration<double>(t - t_last).count());
+    t_last = t;
+  };
   names.build(nl, sv);
+  lap("name tables");
   std::vector<std::uint8_t> is_main(names.chroms.size(), 0);  // header contigs without '_' (mapper.hpp:239-244)
   for (auto const& c : nl.contigs)
     if (c.find('_') == std::string::npos) is_main[names.chrom_id.at(c)] = 1;
+  const std::uint32_t tra_type = names.type_or_none("TRA"), bnd_type = names.type_or_none("BND");
+  auto nl_rec = [&](std::size_t i) { return record_at(nl, names, 0, i, tra_type, bnd_type); };
+  auto sv_rec = [&](std::size_t i) { return record_at(sv, names, 1, i, tra_type, bnd_type); };
+  auto nl_is = [&](std::size_t i, std::uint32_t type) {  // NL record i has this type and sits on a main contig
+    return names.type_of[0][nl.svtype[i]] == type && is_main[names.chrom_of[0][nl.chrom[i]]];
+  };
 
   // ---- DupMapper / InvMapper: overlap join per chromosome ------------------------------------------
   struct Kind { const char* nl_type; const char* sv_type; bool inv; };
@@ -199,14 +233,15 @@ inline Sv2nlOutput map_sv2nl(const VcfTable& nl, const VcfTable& sv, const Optio
     std::vector<Rec> sv_recs, nl_orig, nl_valid;
     std::vector<std::uint32_t> tg, tl, th, qg, ql, qh;
     std::vector<std::uint8_t> qstrand;
+    const std::uint32_t sv_type = names.type_or_none(kind.sv_type), nl_type = names.type_or_none(kind.nl_type);
     for (std::size_t i = 0; i < sv.size(); ++i)
-      if (sv.svtype[i] == kind.sv_type) {
-        sv_recs.push_back(validate_record(record_at(sv, names, i)));  // build_tree validates (mapper.hpp:151)
+      if (names.type_of[1][sv.svtype[i]] == sv_type) {
+        sv_recs.push_back(validate_record(sv_rec(i)));  // build_tree validates (mapper.hpp:151)
         tg.push_back(sv_recs.back().chrom); tl.push_back(sv_recs.back().pos); th.push_back(sv_recs.back().svend);
       }
     for (std::size_t i = 0; i < nl.size(); ++i)
-      if (nl.svtype[i] == kind.nl_type && is_main[names.chrom_id.at(nl.chrom[i])]) {
-        nl_orig.push_back(record_at(nl, names, i));
+      if (nl_is(i, nl_type)) {
+        nl_orig.push_back(nl_rec(i));
         nl_valid.push_back(validate_record(nl_orig.back()));
         qg.push_back(nl_valid.back().chrom); ql.push_back(nl_valid.back().pos); qh.push_back(nl_valid.back().svend);
         qstrand.push_back((std::uint8_t)((nl_valid.back().strand1 ? 1 : 0) | (nl_valid.back().strand2 ? 2 : 0)));
@@ -215,7 +250,9 @@ inline Sv2nlOutput map_sv2nl(const VcfTable& nl, const VcfTable& sv, const Optio
     // surviving pairs, which costs nothing and keeps one definition of the rules next to their citation
     const bcu_filter filter{kind.inv ? (std::uint32_t)BCU_FILTER_SV2NL_INV : (std::uint32_t)BCU_FILTER_SV2NL_DUP,
                             opt.diff, opt.use_strand ? 1u : 0u, 0u};
+    lap(kind.inv ? "inv: select records" : "dup: select records");
     JoinResult jr = gpu_join(opt.device, tg, tl, th, qg, ql, qh, &filter, &qstrand);
+    lap(kind.inv ? "inv: index + join" : "dup: index + join");
     auto check_dup = [&](const Rec& n, const Rec& s) {  // mapper.cpp:50-55
       return is_contained(s, n) && distance_less(n, s, opt.diff);
     };
@@ -227,6 +264,7 @@ inline Sv2nlOutput map_sv2nl(const VcfTable& nl, const VcfTable& sv, const Optio
     };
     if (kind.inv) out.inv = detail::emit_lines(names, nl_orig, nl_valid, sv_recs, jr, check_inv);
     else out.dup = detail::emit_lines(names, nl_orig, nl_valid, sv_recs, jr, check_dup);
+    lap(kind.inv ? "inv: dedup + format" : "dup: dedup + format");
   }
 
   // ---- TraMapper ----------------------------------------------------------------------------------
@@ -243,21 +281,23 @@ inline Sv2nlOutput map_sv2nl(const VcfTable& nl, const VcfTable& sv, const Optio
       return pair_ids.try_emplace({b.c1, b.c2}, (std::uint32_t)pair_ids.size()).first->second;
     };
     for (std::size_t i = 0; i < sv.size(); ++i)
-      if (sv.svtype[i] == "BND") {
-        sv_recs.push_back(record_at(sv, names, i));  // NOT validated (mapper.cpp:158-170)
+      if (names.type_of[1][sv.svtype[i]] == bnd_type) {
+        sv_recs.push_back(sv_rec(i));  // NOT validated (mapper.cpp:158-170)
         auto b = ordered_breakpoints(sv_recs.back());
         tg.push_back(pair_id(b)); tl.push_back(b.p1); th.push_back(b.p1);
       }
     for (std::size_t i = 0; i < nl.size(); ++i)
-      if (nl.svtype[i] == "TRA" && is_main[names.chrom_id.at(nl.chrom[i])]) {
-        nl_orig.push_back(record_at(nl, names, i));
+      if (nl_is(i, tra_type)) {
+        nl_orig.push_back(nl_rec(i));
         nl_valid.push_back(validate_record(nl_orig.back()));
         auto b = ordered_breakpoints(nl_valid.back());
         qg.push_back(pair_id(b));
         ql.push_back(b.p1 > opt.diff ? b.p1 - opt.diff : 0u);
         qh.push_back(b.p1 <= 0xffffffffu - opt.diff ? b.p1 + opt.diff : 0xffffffffu);
       }
+    lap("tra: select records");
     JoinResult jr = gpu_join(opt.device, tg, tl, th, qg, ql, qh);
+    lap("tra: index + join");
     auto check_tra = [&](const Rec& n, const Rec& s) {
       auto a = ordered_breakpoints(n), b = ordered_breakpoints(s);
       if (!(a.c1 == b.c1 && a.c2 == b.c2)) return false;
@@ -265,6 +305,7 @@ inline Sv2nlOutput map_sv2nl(const VcfTable& nl, const VcfTable& sv, const Optio
       return n.pos <= s.svend && s.pos <= n.svend;  // the reference's find_overlaps on the raw intervals
     };
     out.tra = detail::emit_lines(names, nl_orig, nl_valid, sv_recs, jr, check_tra);
+    lap("tra: dedup + format");
   }
   return out;
 }
