@@ -59,7 +59,13 @@ int main(int argc, char** argv) {
     auto secs = [](auto a, auto b) { return std::chrono::duration<double>(b - a).count(); };
     auto t0 = now();
     // CUDA start-up (driver initialisation, context, loading the kernels: seconds on a multi-GPU host)
-    // runs beside the parsing instead of in front of the first join
+    // runs beside the parsing instead of in front of the first join; and unless the user already restricted
+    // the visible devices, only the one device this run uses is exposed to the driver (initialising eight
+    // GPUs costs several times as much as initialising one)
+    if (!std::getenv("CUDA_VISIBLE_DEVICES")) {
+      setenv("CUDA_VISIBLE_DEVICES", std::to_string(opt.device).c_str(), 1);
+      opt.device = 0;
+    }
     double warm_s = 0;
     std::thread cuda_warmup([&] {
       auto w0 = now();
@@ -89,10 +95,10 @@ int main(int argc, char** argv) {
     opt.debug = debug;
     auto res = sv2nl::map_sv2nl(nl, sv, opt);
     auto t2 = now();
-    auto write = [&](const char* ext, const std::vector<std::string>& lines) {
-      std::ofstream ofs(output + ext);
+    auto write = [&](const char* ext, const sv2nl::Lines& lines) {
+      std::ofstream ofs(output + ext, std::ios::binary);
       ofs << sv2nl::HEADER << '\n';
-      for (auto const& l : lines) ofs << l << '\n';
+      ofs.write(lines.text.data(), (std::streamsize)lines.text.size());
     };
     write(".dup", res.dup);
     write(".inv", res.inv);

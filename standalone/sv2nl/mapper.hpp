@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <array>
+#include <charconv>
 #include <chrono>
 #include <cstdio>
 #include <cstdint>
@@ -129,9 +130,17 @@ inline MapKey map_key(const Rec& r) {
   }
   return {r.chrom, 0xffffffffu, r.pos, r.svend};
 }
-inline std::string format_keys(const Rec& r, const Names& names) {  // writer.cpp:21-27 (note pos + 1)
-  std::string c = r.two_chrom ? names.chroms[r.chrom] + "," + names.chroms[r.chr2] : names.chroms[r.chrom];
-  return c + "\t" + std::to_string(r.pos + 1) + "\t" + std::to_string(r.svend) + "\t" + names.types[r.type];
+// writer.cpp:21-27 (note pos + 1), appended to `out` without temporaries
+inline void append_keys(std::string& out, const Rec& r, const Names& names) {
+  out += names.chroms[r.chrom];
+  if (r.two_chrom) { out += ','; out += names.chroms[r.chr2]; }
+  char num[24];
+  out += '\t';
+  out.append(num, std::to_chars(num, num + sizeof(num), (std::uint64_t)r.pos + 1).ptr);
+  out += '\t';
+  out.append(num, std::to_chars(num, num + sizeof(num), r.svend).ptr);
+  out += '\t';
+  out += names.types[r.type];
 }
 
 struct JoinResult {
@@ -177,17 +186,23 @@ struct Options {
   bool debug = false;  // per-mapper phase times on stderr
 };
 
-struct Sv2nlOutput { std::vector<std::string> dup, inv, tra; };
+struct Lines {  // newline-terminated data lines of one output file, in one buffer
+  std::string text;
+  std::size_t count = 0;
+  [[nodiscard]] std::size_t size() const { return count; }
+};
+struct Sv2nlOutput { Lines dup, inv, tra; };
 
 namespace detail {
 // the common tail of the three map_impl loops: post-filter, duplicate-key rule, formatting
 template <class Check>
-std::vector<std::string> emit_lines(const Names& names, const std::vector<Rec>& nl_orig,
-                                    const std::vector<Rec>& nl_valid, const std::vector<Rec>& sv_recs,
-                                    const JoinResult& jr, Check&& check) {
-  std::vector<std::string> lines;
+Lines emit_lines(const Names& names, const std::vector<Rec>& nl_orig, const std::vector<Rec>& nl_valid,
+                 const std::vector<Rec>& sv_recs, const JoinResult& jr, Check&& check) {
+  Lines lines;
   std::unordered_set<MapKey, MapKeyHash> written;  // SV2NL_USE_CACHE: keys of NL records already written
+  written.reserve(nl_orig.size() / 4 + 16);
   std::vector<std::uint32_t> kept;
+  std::string left;
   for (std::size_t q = 0; q < nl_orig.size(); ++q) {
     if (jr.offsets[q] == jr.offsets[q + 1]) continue;  // no raw overlap: nothing can be kept or cached
     const MapKey key = map_key(nl_orig[q]);
@@ -197,8 +212,15 @@ std::vector<std::string> emit_lines(const Names& names, const std::vector<Rec>& 
       if (check(nl_valid[q], sv_recs[jr.targets[k]])) kept.push_back(jr.targets[k]);
     if (kept.empty()) continue;
     written.insert(key);
-    const std::string left = format_keys(nl_orig[q], names);
-    for (auto t : kept) lines.push_back(left + "\t" + format_keys(sv_recs[t], names));
+    left.clear();
+    append_keys(left, nl_orig[q], names);
+    for (auto t : kept) {
+      lines.text += left;
+      lines.text += '\t';
+      append_keys(lines.text, sv_recs[t], names);
+      lines.text += '\n';
+      ++lines.count;
+    }
   }
   return lines;
 }
@@ -233,6 +255,10 @@ inline Sv2nlOutput map_sv2nl(const VcfTable& nl, const VcfTable& sv, const Optio
     std::vector<Rec> sv_recs, nl_orig, nl_valid;
     std::vector<std::uint32_t> tg, tl, th, qg, ql, qh;
     std::vector<std::uint8_t> qstrand;
+    for (auto* v : {&tg, &tl, &th}) v->reserve(sv.size() / 2);
+    for (auto* v : {&qg, &ql, &qh}) v->reserve(nl.size() / 2);
+    sv_recs.reserve(sv.size() / 2); nl_orig.reserve(nl.size() / 2); nl_valid.reserve(nl.size() / 2);
+    qstrand.reserve(nl.size() / 2);
     const std::uint32_t sv_type = names.type_or_none(kind.sv_type), nl_type = names.type_or_none(kind.nl_type);
     for (std::size_t i = 0; i < sv.size(); ++i)
       if (names.type_of[1][sv.svtype[i]] == sv_type) {
@@ -270,33 +296,66 @@ inline Sv2nlOutput map_sv2nl(const VcfTable& nl, const VcfTable& sv, const Optio
   // ---- TraMapper ----------------------------------------------------------------------------------
   // The reference joins on the raw [pos, POS2] intervals of ALL BND records (not validated, chromosome
   // not part of the key) and filters afterwards (mapper.cpp:144-156). Same result with far fewer pairs:
-  // join on the selective condition (group = ordered chromosome pair, target = point p1, query =
-  // [p1 - diff, p1 + diff]) and apply the rest -- second breakpoint, and the reference's raw overlap,
-  // which can still reject a pair -- on the host.
+  // join on the selective conditions -- group = (ordered chromosome pair, bucket of the SECOND breakpoint,
+  // buckets `diff` wide), target = the point p1, query = [p1 - diff, p1 + diff] in each of the three buckets
+  // a partner's p2 can fall into -- and apply the exact rules (both breakpoints within diff, and the
+  // reference's raw-interval overlap, which can still reject a pair) on the host. The three probes of a
+  // record are consecutive queries, so its hits are one contiguous CSR range.
   {
     std::vector<Rec> sv_recs, nl_orig, nl_valid;
     std::vector<std::uint32_t> tg, tl, th, qg, ql, qh;
-    std::map<std::pair<std::uint32_t, std::uint32_t>, std::uint32_t> pair_ids;
-    auto pair_id = [&](const Breakpoints& b) {
-      return pair_ids.try_emplace({b.c1, b.c2}, (std::uint32_t)pair_ids.size()).first->second;
+    const std::uint32_t width = std::max<std::uint32_t>(opt.diff, 1u);
+    const std::uint32_t n_buckets = 0xffffffffu / width + 1u;
+    const std::uint64_t n_chrom = names.chroms.size();
+    std::vector<std::uint32_t> pair_index(n_chrom * n_chrom, 0xffffffffu);  // dense ids of the pairs in use
+    std::uint32_t n_pairs = 0;
+    bool overflow = false;
+    auto group_of = [&](const Breakpoints& b, std::uint32_t bucket) -> std::uint32_t {
+      std::uint32_t& pi = pair_index[(std::uint64_t)b.c1 * n_chrom + b.c2];
+      if (pi == 0xffffffffu) pi = n_pairs++;
+      const std::uint64_t g = (std::uint64_t)pi * n_buckets + bucket;
+      if (g >= 0xffffffffull) overflow = true;  // (pairs x buckets) beyond 32 bits: see the fallback below
+      return (std::uint32_t)g;
     };
+    constexpr std::uint32_t kNoGroup = 0xffffffffu;  // no target carries it: such a probe finds nothing
     for (std::size_t i = 0; i < sv.size(); ++i)
       if (names.type_of[1][sv.svtype[i]] == bnd_type) {
         sv_recs.push_back(sv_rec(i));  // NOT validated (mapper.cpp:158-170)
         auto b = ordered_breakpoints(sv_recs.back());
-        tg.push_back(pair_id(b)); tl.push_back(b.p1); th.push_back(b.p1);
+        tg.push_back(group_of(b, b.p2 / width)); tl.push_back(b.p1); th.push_back(b.p1);
       }
     for (std::size_t i = 0; i < nl.size(); ++i)
       if (nl_is(i, tra_type)) {
         nl_orig.push_back(nl_rec(i));
         nl_valid.push_back(validate_record(nl_orig.back()));
         auto b = ordered_breakpoints(nl_valid.back());
-        qg.push_back(pair_id(b));
-        ql.push_back(b.p1 > opt.diff ? b.p1 - opt.diff : 0u);
-        qh.push_back(b.p1 <= 0xffffffffu - opt.diff ? b.p1 + opt.diff : 0xffffffffu);
+        const std::uint32_t lo = b.p1 > opt.diff ? b.p1 - opt.diff : 0u;
+        const std::uint32_t hi = b.p1 <= 0xffffffffu - opt.diff ? b.p1 + opt.diff : 0xffffffffu;
+        const std::uint32_t mid = b.p2 / width;
+        for (int k = -1; k <= 1; ++k) {
+          const bool exists = !(k < 0 && mid == 0) && !(k > 0 && mid + 1 >= n_buckets);
+          qg.push_back(exists ? group_of(b, (std::uint32_t)((std::int64_t)mid + k)) : kNoGroup);
+          ql.push_back(lo);
+          qh.push_back(hi);
+        }
       }
+    if (overflow) {  // absurdly many chromosome pairs for a tiny diff: fall back to one probe per record
+      for (std::size_t t = 0; t < sv_recs.size(); ++t) {
+        auto b = ordered_breakpoints(sv_recs[t]);
+        tg[t] = pair_index[(std::uint64_t)b.c1 * n_chrom + b.c2];
+      }
+      for (std::size_t q = 0; q < nl_valid.size(); ++q) {
+        auto b = ordered_breakpoints(nl_valid[q]);
+        qg[3 * q] = pair_index[(std::uint64_t)b.c1 * n_chrom + b.c2];
+        qg[3 * q + 1] = qg[3 * q + 2] = kNoGroup;
+      }
+    }
     lap("tra: select records");
-    JoinResult jr = gpu_join(opt.device, tg, tl, th, qg, ql, qh);
+    JoinResult probes = gpu_join(opt.device, tg, tl, th, qg, ql, qh);
+    JoinResult jr;  // per record: the three probes' ranges are adjacent
+    jr.offsets.resize(nl_orig.size() + 1);
+    for (std::size_t q = 0; q <= nl_orig.size(); ++q) jr.offsets[q] = probes.offsets[3 * q];
+    jr.targets = std::move(probes.targets);
     lap("tra: index + join");
     auto check_tra = [&](const Rec& n, const Rec& s) {
       auto a = ordered_breakpoints(n), b = ordered_breakpoints(s);
