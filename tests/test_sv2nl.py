@@ -78,6 +78,66 @@ def test_gpu_mapping_equals_oracle(port_oracle, tmp_path, case):
     assert open(tmp_path / "out.tsv.dup").readline().rstrip("\n") == HEADER == sv2nl_oracle.HEADER
 
 
+# ---- the C++ tool's reader (standalone/sv2nl/vcf_text.hpp) on CPU: same table as the Python reader ------
+CPP_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp")
+
+
+@pytest.fixture(scope="module")
+def dump_vcf():
+    r = subprocess.run(["make", "-C", CPP_DIR, "dump_vcf"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return os.path.join(CPP_DIR, "dump_vcf")
+
+
+def _python_dump(path, source):
+    t = read_vcf(path, source)
+    lines = [f"contig\t{c}" for c in t.contigs]
+    for i in range(len(t)):
+        lines.append(f"rec\t{t.chrom[i]}\t{int(t.pos[i])}\t{int(t.svend[i])}\t{t.svtype[i]}\t{t.chr2[i]}\t"
+                     f"{int(t.strand1[i])}\t{int(t.strand2[i])}")
+    return lines
+
+
+@pytest.mark.parametrize("threads", ["1", "5"])
+def test_cpp_reader_equals_python_reader(dump_vcf, tmp_path, threads):
+    nl_path, sv_path = write_synth_vcfs(str(tmp_path), seed=5, n_sv=4000, n_nl=6000)
+    gz = str(tmp_path / "nl_copy.vcf.gz")
+    import gzip
+    with open(nl_path, "rb") as src, gzip.open(gz, "wb") as dst:
+        dst.write(src.read())
+    env = dict(os.environ, SV2NL_PARSE_THREADS=threads)
+    for path, source in ((NL, "nls"), (SV, "delly"), (nl_path, "nls"), (sv_path, "delly"), (gz, "nls")):
+        r = subprocess.run([dump_vcf, path, source], capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr
+        assert r.stdout.splitlines() == _python_dump(path, source), path
+
+
+def test_cpp_reader_reports_the_offending_line(dump_vcf, tmp_path):
+    head = "##contig=<ID=chr1,length=1000>\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n"
+    good = "chr1\t5\t.\tN\t<DUP>\t.\t.\tSVTYPE=DUP;END=9\n"
+    cases = {
+        "INFO/SVTYPE missing": "chr1\t5\t.\tN\t<DUP>\t.\t.\tEND=9\n",
+        "INFO/POS2 missing": "chr1\t5\t.\tN\t<BND>\t.\t.\tSVTYPE=BND;CHR2=chr2\n",
+        "INFO/CHR2 missing": "chr1\t5\t.\tN\t<BND>\t.\t.\tSVTYPE=BND;POS2=7\n",
+        "fewer than 8 columns": "chr1\t5\t.\tN\n",
+        "POS is not a number": "chr1\tfive\t.\tN\t<DUP>\t.\t.\tSVTYPE=DUP;END=9\n",
+    }
+    for what, bad in cases.items():
+        p = tmp_path / "bad.vcf"
+        p.write_text(head + good * 700 + bad + good * 3)       # line 703 of the file, deep inside a block
+        for threads in ("1", "4"):
+            r = subprocess.run([dump_vcf, str(p), "delly"], capture_output=True, text=True,
+                               env=dict(os.environ, SV2NL_PARSE_THREADS=threads))
+            assert r.returncode == 1 and f"bad.vcf:703: {what}" in r.stderr, (what, threads, r.stderr)
+    # a last line without newline, CRLF line ends and an empty file are all fine
+    p = tmp_path / "tail.vcf"
+    p.write_text(head + good.replace("\n", "\r\n") + good.rstrip("\n"))
+    r = subprocess.run([dump_vcf, str(p), "delly"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.count("rec\t") == 2 and "\r" not in r.stdout
+    p.write_text("")
+    assert subprocess.run([dump_vcf, str(p), "delly"], capture_output=True, text=True).stdout == ""
+
+
 # ---- the C++ tool (standalone/sv2nl): same CLI as the reference's sv2nl ---------------------------------
 import subprocess
 
