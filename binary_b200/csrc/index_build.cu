@@ -9,7 +9,12 @@
 //   lowhigh[r] = {low, high}, id[r]            <- gather
 //   runmax[r]  = max(high[group_begin..r])     <- segmented running max (scan.cu), the "max-end" array
 //   dir[g][b]  = { first row with runmax >= b*W , first row with low >= (b+1)*W , {low, high} of that
-//                first row },  W = 1 << shift: 16 bytes, ONE 128-bit load
+//                first row },  W = 1 << shift (one shift per length class): 16 bytes, ONE 128-bit load
+//   hs[r], dirh[g][b]                          <- second sort on (segment, high): each segment's highs
+//                                                 ascending + the first index with value >= b*W; with them a
+//                                                 long candidate range is COUNTED by two rank lookups
+//                                                 (join.cu count_by_ranks) when the segment has no inverted row
+// and, after this file's build: bcu_index_image_size / export_dev / import_dev (one device blob per index).
 // The directory turns both searches of a query (upper bound of q.high in `low`, lower bound of q.low in
 // `runmax`) into one load when the query lies inside one bin (two otherwise) and brings the first
 // candidate row along; the few rows of slack it admits are rejected by the exact predicate in the scan

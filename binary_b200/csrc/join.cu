@@ -5,9 +5,10 @@
 // (interval_tree.hpp:161-168, 306-334), one recursive pruned walk + vector copies per query, driven
 // once per record by sv2nl (mapper.hpp:207-218).
 //
-// Two launches, no inter-CTA waiting anywhere (a single-pass chained scan was measured first: with
-// ~600 resident tiles of random-latency work every tile ends up waiting for the slowest in-flight
-// predecessor):
+// Separate probe and emit launches, no inter-CTA waiting anywhere (a single-pass chained scan was measured
+// first: with ~600 resident tiles of random-latency work every tile ends up waiting for the slowest
+// in-flight predecessor). The grid is ONE wave (4 CTAs per SM, all resident); K4 and K4b are
+// launched as programmatic dependents of their predecessor.
 //
 //   probe_kernel   K3. The query batch is cut into contiguous chunks, one per CTA; inside a chunk every
 //                  WARP takes 128 consecutive queries at a time (4 per lane, one 128-bit load per input
@@ -17,16 +18,21 @@
 //                            row (the directory replaces both binary searches; index_build.cu)
 //                    count : rows [lb,ub) are a superset of the hits; the exact predicate
 //                            q.low <= t.high && t.low <= q.high (interval_tree.hpp:119-121) is evaluated
-//                            on each. Short ranges: by the owning lane, its 4 queries interleaved so
-//                            their loads overlap, result = a hit bitmask. Long ranges: by the whole warp,
-//                            128 rows per trip with 128-bit loads.
+//                            on each. Short ranges (<= 31 rows): by the owning lane, its 4 queries
+//                            interleaved so their loads overlap, result = a hit bitmask. Long ranges are
+//                            listed per chunk and counted in a second phase of the same kernel, one per
+//                            lane, by rank arithmetic over a second sorted view of the highs
+//                            (count_by_ranks) -- or by a warp scan where a segment has inverted rows, and
+//                            always by a scan under a pair filter.
 //                  Output: per query 8 bytes of state {lb, hit mask | count} (+ the exact end row of long
-//                  ranges) + one hit total per CTA.
+//                  ranges), the chunk's list of long ranges, one hit total per CTA.
 //   emit_kernel    K4. Same chunks. A CTA first sums the totals of the chunks before its own (its
 //                  global base), then walks its chunk 1024 queries at a time: counts from the state ->
 //                  warp scan + one barrier -> u64 CSR offsets, in query order; short-range hits are staged
 //                  in shared memory at their rank, gathered to target ids, and written to consecutive
-//                  addresses; long ranges are re-scanned by the warp with ballot/popc compaction.
+//                  addresses.
+//   emit_long_kernel K4b. The pairs of the listed long ranges: a warp per range, one row per lane, ballot =
+//                  rank, compacted stores (filtered long ranges are emitted by K4 itself).
 //
 //   direct_kernel  the two-call ABI's second half (offsets supplied by the caller) and the any-overlap
 //                  bit: bounds + scan + scatter without any prefix step.
