@@ -120,6 +120,26 @@ def ncu_traffic(workload: str):
         return None
 
 
+def pin_to_gpu_numa_node(local: int):
+    """N > 1: run this rank on the CPUs next to its GPU (NVML's affinity mask), so that the pinned host
+    buffers of the e2e leg are first-touched on the GPU's NUMA node instead of wherever the launcher put the
+    process. Returns the number of CPUs in the mask, or None when NVML does not answer."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1]
+        allowed = set(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def cpu_sample_size(workload: str, n_q: int) -> int:
     """Queries the CPU reference is timed on: ~10-30 core-seconds of work. B (0.65 hits/query, ~1 us per
     query and core) runs the WHOLE batch; C (83 hits/query, ~500 us per query and core) and D are sampled."""
@@ -187,6 +207,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the overlap join has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = pin_to_gpu_numa_node(local) if world > 1 else None
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -330,7 +351,7 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": w.name, "n_targets": n_t, "queries_per_gpu": n_q,
-                       "hits_per_query": n_hits / n_q, "sharding": "replicated index, contiguous query range per GPU, no collective",
+                       "hits_per_query": n_hits / n_q, "sharding": "replicated index, contiguous query range per GPU, no collective", "numa_cpus_per_rank": numa,
                        "l2": "flushed between timed steps (512 MiB write, not timed); step working set ~280 MB > 126 MB L2",
                        "timing": "CUDA events per step on the launching stream, summed; max over ranks",
                        "index": info},
