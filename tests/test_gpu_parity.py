@@ -417,3 +417,45 @@ def test_long_ranges_rank_count_and_its_fallbacks(port_oracle, label):
         c["qh"] = np.minimum(c["ql"].astype(np.uint64) + 30000, 0xFFFFFFFF).astype(np.uint32)
     hits = _check_all_entry_points(c, port_oracle)
     assert hits > 30 * c["ql"].size or label in ("inverted_queries", "length_classes", "point_targets")
+
+
+@pytest.mark.parametrize("cap", [0, 1, 37, 5000])
+def test_pair_capacity_never_writes_past_the_buffer(port_oracle, cap):
+    """bcu_join_dev with a pair buffer smaller than the result: offsets and total are complete, positions
+    below the capacity hold correct pairs, nothing at or beyond the capacity is touched (sentinel check) --
+    on a batch that mixes short ranges with long ones (emit_kernel and emit_long_kernel both clip)."""
+    import torch
+    c = random_case(9, n_t=20000, n_q=600, span=200000, max_len=60000)          # long ranges
+    s = random_case(10, n_t=20000, n_q=600, span=200000, max_len=30)            # short ranges, same span
+    ql = np.stack([c["ql"], s["ql"]], axis=1).reshape(-1).copy()                # interleaved
+    qh = np.stack([c["qh"], s["qh"]], axis=1).reshape(-1).copy()
+    f = port_oracle.build(c["tl"], c["th"], None)
+    want_off, want_tid = f.query_sorted_pairs(ql, qh, None, threads=4)
+    total = int(want_off[-1])
+    assert total > 5000
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).to(dev)
+    d_tl, d_th, d_ql, d_qh = t(c["tl"]), t(c["th"]), t(ql), t(qh)
+    stream = torch.cuda.current_stream().cuda_stream
+    ix = DeviceIndex.build_dev(c["tl"].size, d_tl.data_ptr(), d_th.data_ptr(), stream=stream)
+    n = ql.size
+    d_off = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    d_hq = torch.full((cap + 4096,), -1, dtype=torch.int32, device=dev)
+    d_ht = torch.full((cap + 4096,), -1, dtype=torch.int32, device=dev)
+    d_total = torch.zeros(1, dtype=torch.int64, device=dev)
+    ix.join_dev(n, d_ql.data_ptr(), d_qh.data_ptr(), d_off.data_ptr(), cap, d_hq.data_ptr(), d_ht.data_ptr(),
+                d_total.data_ptr(), 0, 0, stream)
+    torch.cuda.synchronize()
+    assert int(d_total.item()) == total
+    assert np.array_equal(d_off.cpu().numpy().view(np.uint64), want_off)
+    hq, ht = d_hq.cpu().numpy(), d_ht.cpu().numpy()
+    assert (hq[cap:] == -1).all() and (ht[cap:] == -1).all()                    # untouched beyond the capacity
+    want_q = np.repeat(np.arange(n, dtype=np.int64), np.diff(want_off).astype(np.int64))
+    assert np.array_equal(hq[:cap].astype(np.int64), want_q[:cap])
+    for q in np.unique(want_q[:cap]):                                            # per query: a subset, no repeats
+        a, b = int(want_off[q]), int(want_off[q + 1])
+        got = ht[a:min(b, cap)].view(np.uint32)
+        assert np.unique(got).size == got.size and np.isin(got, want_tid[a:b]).all()
+        if b <= cap:
+            assert np.array_equal(np.sort(got), want_tid[a:b])
+    ix.close()
