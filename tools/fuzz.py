@@ -33,8 +33,8 @@ for s in range(seed0, seed0 + n_cases):
     ok = ok and np.array_equal(ix.any(c["ql"], c["qh"], c["qg"]), np.diff(want_off) > 0)
     info = ix.info(); ix.close()
     pairs += int(want_off[-1])
-    if (s - seed0 + 1) % 10 == 0:
-        print(f"... {s - seed0 + 1} cases OK, {pairs} pairs, {time.time()-t0:.0f} s", flush=True)
     if not ok:
         print(f"MISMATCH seed {s} {kw} index {info}", flush=True); sys.exit(1)
+    if (s - seed0 + 1) % 10 == 0:
+        print(f"... {s - seed0 + 1} cases OK, {pairs} pairs, {time.time()-t0:.0f} s", flush=True)
 print(f"fuzz OK: {n_cases} cases from seed {seed0}, {pairs} pairs compared, {time.time()-t0:.1f} s")
