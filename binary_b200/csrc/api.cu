@@ -49,6 +49,12 @@ struct Staging {
   }
 };
 
+static int guard_ok(const DeviceGuard& g, int device) {
+  if (g.ok) return BCU_OK;
+  set_error("cannot select CUDA device %d: %s", device, cudaGetErrorString(cudaGetLastError()));
+  return BCU_E_CUDA;
+}
+
 static int check_query_args(const char* fn, const bcu_index* ix, uint64_t n_q, const uint32_t* qlow,
                             const uint32_t* qhigh) {
   if (!ix) { set_error("%s: index is NULL", fn); return BCU_E_INVALID; }
@@ -91,6 +97,7 @@ extern "C" int bcu_query_count_dev(const bcu_index* ix, uint64_t n_q, const uint
   BCU_TRY(check_query_args("bcu_query_count_dev", ix, n_q, d_qlow, d_qhigh));
   if (!d_offsets) { set_error("bcu_query_count_dev: d_offsets is NULL"); return BCU_E_INVALID; }
   DeviceGuard guard(ix->device);
+  BCU_TRY(guard_ok(guard, ix->device));
   return launch_join(ix, kModeCount, n_q, d_qgroup, d_qlow, d_qhigh, d_offsets, 0, nullptr, nullptr,
                      nullptr, nullptr, 0, static_cast<cudaStream_t>(stream));
 }
@@ -105,6 +112,7 @@ extern "C" int bcu_query_scatter_dev(const bcu_index* ix, uint64_t n_q, const ui
     return BCU_E_INVALID;
   }
   DeviceGuard guard(ix->device);
+  BCU_TRY(guard_ok(guard, ix->device));
   return launch_join(ix, kModeScatter, n_q, d_qgroup, d_qlow, d_qhigh, const_cast<uint64_t*>(d_offsets), 0,
                      d_hit_query, d_hit_target, nullptr, nullptr, 0, static_cast<cudaStream_t>(stream));
 }
@@ -119,6 +127,7 @@ extern "C" int bcu_join_dev(const bcu_index* ix, uint64_t n_q, const uint32_t* d
     return BCU_E_INVALID;
   }
   DeviceGuard guard(ix->device);
+  BCU_TRY(guard_ok(guard, ix->device));
   return launch_join(ix, kModeFused, n_q, d_qgroup, d_qlow, d_qhigh, d_offsets, pair_capacity, d_hit_query,
                      d_hit_target, d_total, nullptr, query_id_base, static_cast<cudaStream_t>(stream));
 }
@@ -138,6 +147,7 @@ extern "C" int bcu_join_filtered_dev(const bcu_index* ix, const bcu_filter* filt
     return BCU_E_INVALID;
   }
   DeviceGuard guard(ix->device);
+  BCU_TRY(guard_ok(guard, ix->device));
   return launch_join(ix, kModeFused, n_q, d_qgroup, d_qlow, d_qhigh, d_offsets, pair_capacity, d_hit_query,
                      d_hit_target, d_total, nullptr, query_id_base, static_cast<cudaStream_t>(stream), nullptr,
                      filter, d_qstrand);
@@ -149,6 +159,7 @@ extern "C" int bcu_query_any_dev(const bcu_index* ix, uint64_t n_q, const uint32
   BCU_TRY(check_query_args("bcu_query_any_dev", ix, n_q, d_qlow, d_qhigh));
   if (n_q && !d_any) { set_error("bcu_query_any_dev: d_any is NULL"); return BCU_E_INVALID; }
   DeviceGuard guard(ix->device);
+  BCU_TRY(guard_ok(guard, ix->device));
   return launch_join(ix, kModeAny, n_q, d_qgroup, d_qlow, d_qhigh, nullptr, 0, nullptr, nullptr, nullptr,
                      d_any, 0, static_cast<cudaStream_t>(stream));
 }
@@ -160,6 +171,7 @@ extern "C" int bcu_query_count(const bcu_index* ix, uint64_t n_q, const uint32_t
   BCU_TRY(check_query_args("bcu_query_count", ix, n_q, qlow, qhigh));
   if (!offsets) { set_error("bcu_query_count: offsets is NULL"); return BCU_E_INVALID; }
   DeviceGuard guard(ix->device);
+  BCU_TRY(guard_ok(guard, ix->device));
   Staging st;
   BCU_TRY(st.init());
   uint32_t *d_g, *d_l, *d_h;
@@ -188,6 +200,7 @@ extern "C" int bcu_query_scatter(const bcu_index* ix, uint64_t n_q, const uint32
   }
   if (n_q == 0 || total == 0) return BCU_OK;
   DeviceGuard guard(ix->device);
+  BCU_TRY(guard_ok(guard, ix->device));
   Staging st;
   BCU_TRY(st.init());
   uint32_t *d_g, *d_l, *d_h, *d_hq, *d_ht;
@@ -212,6 +225,7 @@ extern "C" int bcu_query_any(const bcu_index* ix, uint64_t n_q, const uint32_t* 
   if (n_q && !any) { set_error("bcu_query_any: any is NULL"); return BCU_E_INVALID; }
   if (n_q == 0) return BCU_OK;
   DeviceGuard guard(ix->device);
+  BCU_TRY(guard_ok(guard, ix->device));
   Staging st;
   BCU_TRY(st.init());
   uint32_t *d_g, *d_l, *d_h;

@@ -238,7 +238,10 @@ static double env_double(const char* name, double dflt) {
 }
 
 static void free_index_members(bcu_index* ix) {
-  // index arrays live in the stream-ordered pool (see alloc_rows): freed on the legacy default stream
+  // Index arrays live in the stream-ordered pool (see alloc_rows). *_dev queries are asynchronous and may
+  // still be reading them on streams the legacy default stream does not wait for (cudaStreamNonBlocking,
+  // e.g. PyTorch side streams): drain the device first, as a classic cudaFree would have done.
+  cudaDeviceSynchronize();
   cudaFreeAsync(ix->d_lowhigh, nullptr);
   cudaFreeAsync(ix->d_id, nullptr);
   cudaFreeAsync(ix->d_high, nullptr);
@@ -591,7 +594,7 @@ extern "C" int bcu_index_build(int device, uint64_t n_t, const uint32_t* group, 
 
 extern "C" int bcu_index_free(bcu_index* ix) {
   if (!ix) return BCU_OK;
-  DeviceGuard guard(ix->device);
+  DeviceGuard guard(ix->device);  // (if the device cannot be selected the frees fail harmlessly)
   free_index_members(ix);
   delete ix;
   return BCU_OK;

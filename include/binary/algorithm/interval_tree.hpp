@@ -21,7 +21,14 @@
 //   * the overlap predicate is the reference's BaseInterval::is_overlap, fixed: low <= o.high &&
 //     o.low <= high (interval_tree.hpp:119-121). A subclass overriding the virtual is NOT consulted on
 //     the device.
-//   * hits of one query are ordered by (low, insertion ordinal) instead of tree-shape preorder.
+//   * find_overlaps returns the hits of a query sorted by (low, insertion ordinal) instead of tree-shape
+//     preorder, and find_overlap returns the FIRST of that order (the reference returns whichever overlap its
+//     root descent meets first, interval_tree.hpp:291-304). The batched entry point returns target ids in the
+//     device's order, which is unspecified inside one query (it depends on the index's length classes).
+//   * cost model: every single find_overlaps / find_overlap call is one host->device->host round trip
+//     (tens of microseconds), and an insert after a query rebuilds the whole device index. Callers that loop
+//     over records should collect them and call find_overlaps_batch once; after kUnbatchedHint single
+//     queries the header says so once on stderr (set BINARY_CUDA_QUIET to silence it).
 //   * errors: the reference tree never throws; this one throws binary::cuda_error when the CUDA
 //     library reports a failure (there is no CPU fallback).
 //   * lvalue interval arguments are accepted as well (the reference only compiles for rvalues/args).
@@ -32,9 +39,13 @@
 
 #include <binary_cuda.h>
 
+#include <algorithm>
+#include <atomic>
 #include <cassert>
 #include <concepts>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <memory>
 #include <mutex>
 #include <optional>
@@ -172,8 +183,22 @@ namespace algorithm::tree {
     using pointer = std::unique_ptr<NodeType>;
 
     explicit IntervalTree(int device = 0) : device_{device} {}
-    IntervalTree(IntervalTree&&) noexcept = default;
-    IntervalTree& operator=(IntervalTree&&) noexcept = default;
+    // moves leave the source empty but usable (it gets a mutex of its own again)
+    IntervalTree(IntervalTree&& o) noexcept
+        : device_{o.device_}, items_{std::move(o.items_)}, index_{std::move(o.index_)}, mutex_{std::move(o.mutex_)} {
+      o.items_.clear();
+      o.mutex_ = std::make_unique<std::mutex>();
+    }
+    IntervalTree& operator=(IntervalTree&& o) noexcept {
+      if (this != &o) {
+        device_ = o.device_;
+        items_ = std::move(o.items_);
+        index_ = std::move(o.index_);
+        o.items_.clear();
+        o.index_.reset();
+      }
+      return *this;
+    }
     IntervalTree(IntervalTree const&) = delete;
     IntervalTree& operator=(IntervalTree const&) = delete;
     virtual ~IntervalTree() = default;
@@ -205,7 +230,9 @@ namespace algorithm::tree {
     // ---- single queries (reference: interval_tree.hpp:152-168) -------------------------------------
     [[nodiscard]] auto find_overlaps(interval_type const& interval) const -> std::vector<interval_type> {
       const std::uint32_t ql = detail::to_device_key(interval.low), qh = detail::to_device_key(interval.high);
+      note_single_query();
       auto res = batch(1, &ql, &qh);
+      sort_hits(res.target_ids);
       std::vector<interval_type> out;
       out.reserve(res.target_ids.size());
       for (auto id : res.target_ids) out.push_back(items_[id]);
@@ -219,9 +246,14 @@ namespace algorithm::tree {
     }
 
     [[nodiscard]] auto find_overlap(interval_type const& interval) const -> std::optional<interval_type> {
-      auto all = find_overlaps(interval);
-      if (all.empty()) return {};
-      return std::move(all.front());
+      // deterministic whatever the index layout: the hit with the smallest (low, insertion ordinal)
+      const std::uint32_t ql = detail::to_device_key(interval.low), qh = detail::to_device_key(interval.high);
+      note_single_query();
+      auto res = batch(1, &ql, &qh);
+      if (res.target_ids.empty()) return {};
+      const auto best = *std::min_element(res.target_ids.begin(), res.target_ids.end(),
+                                          [&](std::uint32_t a, std::uint32_t b) { return hit_less(a, b); });
+      return items_[best];
     }
 
     template <typename... Args>
@@ -256,7 +288,24 @@ namespace algorithm::tree {
       }
     }
 
+    static constexpr std::uint64_t kUnbatchedHint = 4096;
+
   private:
+    [[nodiscard]] bool hit_less(std::uint32_t a, std::uint32_t b) const {
+      return items_[a].low != items_[b].low ? items_[a].low < items_[b].low : a < b;
+    }
+    void sort_hits(std::vector<std::uint32_t>& ids) const {
+      std::sort(ids.begin(), ids.end(), [&](std::uint32_t a, std::uint32_t b) { return hit_less(a, b); });
+    }
+    // the drop-in's cost model differs from the reference's (see the header comment): say so once
+    static void note_single_query() {
+      static std::atomic<std::uint64_t> calls{0};
+      if (calls.fetch_add(1, std::memory_order_relaxed) + 1 == kUnbatchedHint && !std::getenv("BINARY_CUDA_QUIET"))
+        std::fprintf(stderr,
+                     "binary::IntervalTree (CUDA): %llu single find_overlap(s) calls so far, each a full "
+                     "host<->device round trip; collect the queries and call find_overlaps_batch once\n",
+                     static_cast<unsigned long long>(kUnbatchedHint));
+    }
     template <typename... Args> static auto make_query(Args&&... args) -> interval_type {
       return interval_type{std::forward<Args>(args)...};
     }

@@ -96,6 +96,9 @@ int bcu_index_build(int device, uint64_t n_t, const uint32_t* group, const uint3
                     const uint32_t* high, bcu_index** out);
 int bcu_index_build_dev(int device, uint64_t n_t, const uint32_t* d_group, const uint32_t* d_low,
                         const uint32_t* d_high, void* stream, bcu_index** out);
+/* Lifetime: bcu_index_free synchronises the index's device before releasing its memory, so *_dev work
+ * still queued on ANY stream of that device finishes first (the call therefore blocks; it is not for
+ * hot loops). Do not call it concurrently with a query on the same index from another host thread. */
 int bcu_index_free(bcu_index* index);
 int bcu_index_size(const bcu_index* index, uint64_t* n_t);
 int bcu_index_get_info(const bcu_index* index, bcu_index_info* info);

@@ -15,15 +15,15 @@ def _run(*args):
 
 
 def test_reference_arm_json_line():
-    r = _run("--impl", "reference", "--steps", "1", "--warmup", "1", "--queries", "50000", "--targets", "20000")
+    r = _run("--impl", "reference", "--steps", "1", "--warmup", "1", "--queries", "50000", "--targets", "20000")   # default workload: D
     assert r.returncode == 0, r.stderr
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "overlap_queries_per_sec" and d["unit"] == "queries/s"
-    assert d["n_gpus"] == 1 and d["steps"] == 1 and d["higher_is_better"] is True and d["scaling"] == "weak"
+    assert d["n_gpus"] == 1 and d["steps"] == 1 and d["higher_is_better"] is True and d["scaling"] == "strong"
     assert d["vs_baseline"] is None and d["dtype"] == "u32" and d["data"] == "synthetic"
-    assert d["config"]["workload"].startswith("B:") and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["config"]["workload"].startswith("D:") and d["value"] > 0 and d["ms_per_step"] > 0
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     e = d["e2e"]
