@@ -5,8 +5,12 @@ image; the north star keeps that parser on the host, so this is only the shim SU
 for at that boundary. It honours exactly the fields sv2nl reads:
 
 * ``chrom``  = column 1; ``pos`` = POS - 1 (0-based, ``vcf.hpp:305-310``, ``test_vcf.cpp:100``)
-* INFO ``SVTYPE`` (required), ``CHR2`` for TRA/BND, ``STRAND1``/``STRAND2`` == "+" for INV (missing =>
-  stays True), end coordinate = ``POS2`` if SVTYPE == BND, else ``SVEND`` when the source is "nls", else
+* INFO ``SVTYPE`` (required), ``CHR2`` for TRA/BND, ``STRAND1``/``STRAND2`` == "+" for INV. The reference
+  updates ONE record object in place while it iterates (``vcf.hpp:262-275,305-310``) and swallows the
+  exception of a missing strand tag (``vcf_info.cpp:17-31``), so an INV record without ``STRAND1`` keeps BOTH
+  strands of the previous INV record of the file (initially "+","+"), and one with ``STRAND1`` but without
+  ``STRAND2`` keeps the previous ``strand2``. The same carry is applied here (pinned against the unmodified
+  reference in tests/test_sv2nl_reference.py). End coordinate = ``POS2`` if SVTYPE == BND, else ``SVEND`` when the source is "nls", else
   ``END`` (``standalone/sv2nl/source/vcf_info.cpp:9-43``); the end stays the raw 1-based INFO integer while
   ``pos`` is 0-based -- the reference does not reconcile them and neither do we.
 * contig list = ``##contig=<ID=...>`` header lines in order (``vcf.hpp:577-589``)
@@ -58,6 +62,7 @@ def read_vcf(path: str, source: str) -> VcfTable:
     """``source`` = "nls" (ScanNLS non-linear calls, end in SVEND) or "delly" (end in END / POS2)."""
     contigs: List[str] = []
     chrom, pos, svend, svtype, chr2, s1, s2 = [], [], [], [], [], [], []
+    carry1 = carry2 = True  # Sv2nlInfoField's defaults (vcf_info.hpp:20-21)
     with _open(path) as fh:
         for line_no, line in enumerate(fh, 1):
             if line.startswith("##contig=<"):
@@ -82,12 +87,11 @@ def read_vcf(path: str, source: str) -> VcfTable:
                 if "CHR2" not in info:
                     raise VcfReaderError(f"{path}:{line_no}: INFO/CHR2 missing")
                 c2 = info["CHR2"]
-            st1 = st2 = True
-            if t == "INV":  # failures are swallowed in the reference: a missing key keeps the default
-                if "STRAND1" in info:
-                    st1 = info["STRAND1"] == "+"
-                    if "STRAND2" in info:
-                        st2 = info["STRAND2"] == "+"
+            if t == "INV" and "STRAND1" in info:  # a missing tag keeps what the previous INV record left
+                carry1 = info["STRAND1"] == "+"
+                if "STRAND2" in info:
+                    carry2 = info["STRAND2"] == "+"
+            st1, st2 = carry1, carry2
             chrom.append(cols[0])
             pos.append(int(cols[1]) - 1)
             svend.append(int(info[end_key]))

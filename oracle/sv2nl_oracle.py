@@ -9,10 +9,12 @@ Follows the reference line by line (paths relative to /root/reference/standalone
   run(): the three mappers and their types           source/main.cpp:46-81
 over the ORACLE interval tree (one tree per chromosome for Dup/Inv, one tree for Tra).
 
-PARITY UNPINNED at this level: the reference has no sv2nl tests or golden outputs, and sv2nl itself
-cannot be built here (htslib absent), so this restatement is pinned only by reading the source. The join
-underneath it IS pinned (oracle/interval_oracle.c against the reference's known answers and against the
-unmodified reference headers).
+PARITY PINNED (round 2): the reference has no sv2nl tests or golden outputs of its own, but its sv2nl
+sources compile here unmodified over a text-VCF stand-in for htslib (oracle/_ref/libsv2nl_ref.so, see
+oracle/sv2nl_ref_harness.cpp and oracle/stubs/). tests/test_sv2nl_reference.py checks this restatement
+against it predicate by predicate and as whole runs of the reference tool (fixture + synthetic VCFs, incl.
+the strand carry-over of the reference reader); tests/golden/sv2nl_expected.json is the reference tool's own
+output. What remains this repo's reading is only htslib's field extraction (oracle/stubs/htslib_text.cpp).
 """
 from __future__ import annotations
 

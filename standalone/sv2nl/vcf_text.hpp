@@ -113,6 +113,24 @@ inline bool parse_i64(std::string_view s, long long& out) {
 }  // namespace detail
 
 namespace detail {
+constexpr std::uint8_t kInherit = 2;
+// Sequential pass over the finished table: an INV record without STRAND1 keeps both strands of the previous
+// INV record (initially '+','+'), one with STRAND1 but without STRAND2 keeps the previous strand2; records of
+// other types show the carried values too, as the reference's in-place record does.
+inline void carry_strands(VcfTable& t) {
+  std::uint32_t inv = 0xffffffffu;
+  for (std::size_t k = 0; k < t.type_names.size(); ++k)
+    if (t.type_names[k] == "INV") inv = (std::uint32_t)k;
+  std::uint8_t c1 = 1, c2 = 1;
+  for (std::size_t i = 0; i < t.size(); ++i) {
+    if (t.svtype[i] == inv && t.strand1[i] != kInherit) {
+      c1 = t.strand1[i];
+      if (t.strand2[i] != kInherit) c2 = t.strand2[i];
+    }
+    t.strand1[i] = c1;
+    t.strand2[i] = c2;
+  }
+}
 // Parses whole lines of VCF text into `t` through the given interners. n_lines: lines seen. Returns an
 // empty string, or the error, with bad_line = 1-based index of the offending line within `text`.
 inline std::string parse_lines(std::string_view text, bool nls, VcfTable& t, Interner& chroms, Interner& types,
@@ -156,8 +174,11 @@ inline std::string parse_lines(std::string_view text, bool nls, VcfTable& t, Int
       if (!info.chr2.data()) return fail("INFO/CHR2 missing");
       c2 = chroms.id(info.chr2);
     }
-    std::uint8_t s1 = 1, s2 = 1;
-    if (type == "INV" && info.strand1.data()) {  // a missing STRAND1 keeps both defaults (vcf_info.cpp:17-31)
+    // 0 = '-', 1 = '+', kInherit = "whatever the previous INV record of the file left" (resolved by
+    // carry_strands once all pieces are in file order): the reference updates one record object in place and
+    // swallows the exception of a missing strand tag (vcf.hpp:305-310, vcf_info.cpp:17-31)
+    std::uint8_t s1 = kInherit, s2 = kInherit;
+    if (type == "INV" && info.strand1.data()) {
       s1 = info.strand1 == "+";
       if (info.strand2.data()) s2 = info.strand2 == "+";
     }
@@ -288,6 +309,7 @@ inline VcfTable read_vcf(const std::string& path, std::string_view source) {
     have -= whole;
   }
   gzclose(f);
+  detail::carry_strands(t);
   return t;
 }
 

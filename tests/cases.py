@@ -77,6 +77,11 @@ SYNTH_CONTIGS = [("chr1", 2_000_000), ("chr2", 1_500_000), ("chr10", 1_200_000),
                  ("chrUn_KI270302v1", 2274), ("chr1_KI270706v1_random", 175055)]
 
 
+# htslib types INFO values by the header's ##INFO lines (an undeclared tag is a String: asking for END as an
+# integer then fails), so every generated VCF declares what sv2nl reads (vcf_info.cpp:10-42)
+VCF_INFO_HEADER = ['##INFO=<ID=SVTYPE,Number=1,Type=String,Description="Type of structural variant">', '##INFO=<ID=CHR2,Number=1,Type=String,Description="Chromosome for the second breakpoint">', '##INFO=<ID=END,Number=1,Type=Integer,Description="End position of the structural variant">', '##INFO=<ID=POS2,Number=1,Type=Integer,Description="Position of the second breakpoint (BND)">', '##INFO=<ID=SVEND,Number=1,Type=Integer,Description="2nd position of the structural variant">', '##INFO=<ID=STRAND1,Number=1,Type=String,Description="Strand for breakpoint1">', '##INFO=<ID=STRAND2,Number=1,Type=String,Description="Strand for breakpoint2">']
+
+
 def write_synth_vcfs(directory, seed=1, n_sv=3000, n_nl=2000):
     """Delly-style SV VCF (DUP/INV/BND/DEL) + ScanNLS-style NL VCF (TDUP/INV/TRA/INS). NL records are
     jittered copies of SV records (so the filters see near hits, containments, strand cases, duplicates,
@@ -86,6 +91,7 @@ def write_synth_vcfs(directory, seed=1, n_sv=3000, n_nl=2000):
     names = [c for c, _ in SYNTH_CONTIGS]
     lens = dict(SYNTH_CONTIGS)
     head = ["##fileformat=VCFv4.2"] + [f"##contig=<ID={c},length={l}>" for c, l in SYNTH_CONTIGS]
+    head += VCF_INFO_HEADER
     head.append("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO")
     sv_lines, nl_lines, sv_recs = [], [], []
     for i in range(n_sv):

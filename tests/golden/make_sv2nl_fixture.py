@@ -10,6 +10,7 @@ import re
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = "/root/reference/test/data/debug.vcf.gz"
 KEEP = ("SVTYPE", "CHR2", "SVEND", "STRAND1", "STRAND2")
+INFO_HEADER = ['##INFO=<ID=SVTYPE,Number=1,Type=String,Description="Type of structural variant">', '##INFO=<ID=CHR2,Number=1,Type=String,Description="Chromosome for the second breakpoint">', '##INFO=<ID=END,Number=1,Type=Integer,Description="End position of the structural variant">', '##INFO=<ID=POS2,Number=1,Type=Integer,Description="Position of the second breakpoint (BND)">', '##INFO=<ID=SVEND,Number=1,Type=Integer,Description="2nd position of the structural variant">', '##INFO=<ID=STRAND1,Number=1,Type=String,Description="Strand for breakpoint1">', '##INFO=<ID=STRAND2,Number=1,Type=String,Description="Strand for breakpoint2">']
 
 out = ["##fileformat=VCFv4.3", "##source=ScanNLS (reduced copy of BINARY test/data/debug.vcf.gz)"]
 extra = 0
@@ -22,6 +23,7 @@ with gzip.open(SRC, "rt") as fh:
             elif extra < 3:
                 out.append(line.strip()); extra += 1
         elif line.startswith("#CHROM"):
+            out.extend(INFO_HEADER)   # htslib types INFO values by these lines (undeclared tags become String)
             out.append("\t".join(line.strip().split("\t")[:8]))
         elif not line.startswith("#"):
             c = line.rstrip("\n").split("\t")
