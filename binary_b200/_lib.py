@@ -36,7 +36,7 @@ FILTER_NONE, FILTER_SV2NL_DUP, FILTER_SV2NL_INV = 0, 1, 2
 class IndexInfo(C.Structure):
     _fields_ = [("n_targets", C.c_uint64), ("n_groups", C.c_uint32), ("n_components", C.c_uint32),
                 ("bin_shift", C.c_uint32), ("sort_passes", C.c_uint32), ("n_bins", C.c_uint64),
-                ("device_bytes", C.c_uint64), ("device", C.c_int32), ("reserved", C.c_int32)]
+                ("device_bytes", C.c_uint64), ("device", C.c_int32), ("binned_tiles", C.c_int32)]
 
 
 # every symbol include/binary_cuda.h declares: name -> (restype, argtypes)

@@ -75,6 +75,43 @@ struct __align__(16) DirEntry {
 };
 constexpr uint32_t kInlineRows = 1;
 
+// ---- bin layout: the index cut into shared-memory sized coordinate tiles (binned_join.cu) ----------------
+// A BIN is a run of consecutive coordinate cells (width 1 << cell_shift) of one group whose rows -- over all
+// length classes, including for each class the rows that start up to that class's maximum length before the
+// bin -- fit one CTA's shared memory. Queries are routed to the bin of their `low`.
+constexpr uint32_t kBinMaxClasses = 4;
+constexpr uint32_t kBinRowsCap = 13312;     // rows of one bin's tile (all classes): 12 B each = 156 KB
+constexpr uint32_t kBinLutCap = 12288;      // u16 entries of the per-class sub-cell tables of one tile
+constexpr uint32_t kBinMaxCells = 16384;    // cells over all groups: the routing table is staged in shared memory
+constexpr uint32_t kBinMaxBins = 4095;      // bin ids are u16; kBinNull = no bin (unknown group / beyond every row)
+constexpr uint32_t kBinNull = 0xFFFFu;
+
+struct BinClass {
+  uint32_t row0;     // first global row copied into the tile (multiple of 4: bulk copies move 16-byte units)
+  uint32_t n_copy;   // rows copied (multiple of 4)
+  uint32_t lo, hi;   // valid tile-relative rows [lo, hi): lo = first row of the segment with low >= x0,
+                     // hi = first row with low >= the bin's end (segment end for a group's last bin)
+  uint32_t x0;       // coordinate origin of the sub-cell table: max(bin begin - maxlen, 0)
+  uint32_t ls;       // log2 of the sub-cell width
+  uint32_t nsub;     // sub-cells; the table has nsub + 1 entries
+  uint32_t maxlen;   // no proper row of the class is longer (high - low): bounds the candidate window
+  uint32_t s_off;    // offset of the class's rows in the tile's row arrays
+  uint32_t lut_off;  // offset of the class's table in the tile's LUT
+};
+struct BinDesc {
+  uint32_t group;    // index of the group in the sorted group table
+  uint32_t x_begin;  // first coordinate of the bin
+  uint32_t x_end;    // first coordinate past the bin; 0 = the group's last bin (no upper limit)
+  uint32_t n_rows;   // rows copied over all classes
+  BinClass cls[kBinMaxClasses];
+};
+struct BinGroup {    // query routing, per group (same order as the GroupDesc table)
+  uint32_t gval;
+  uint32_t cell_base;  // first entry of the group in cell2bin
+  uint32_t n_cells;    // cells of the group; a query whose low lies beyond them cannot hit anything
+  uint32_t pad;
+};
+
 }  // namespace bcu
 
 struct bcu_index {
@@ -97,6 +134,13 @@ struct bcu_index {
   bcu::DirEntry* d_dir = nullptr;    // [n_bins] see DirEntry
   uint32_t* d_hs = nullptr;          // [n]   `high` of each segment's rows sorted ASCENDING (same row ranges)
   uint32_t* d_dirh = nullptr;        // [n_bins] first index of the segment's slice of d_hs with value >= b*W
+  uint32_t max_len = 0;              // longest proper target (high - low): window bound of the top length class
+  // bin layout (binned_join.cu); bn_bins == 0: the index is not eligible for the binned path
+  uint32_t bn_bins = 0, bn_cells = 0, bn_cell_shift = 0;
+  uint32_t* d_low = nullptr;           // [n+4] `low` of the sorted rows as a plain column (tile copies)
+  bcu::BinDesc* d_bn_desc = nullptr;   // [bn_bins]
+  bcu::BinGroup* d_bn_groups = nullptr;  // [n_groups]
+  uint16_t* d_bn_cell2bin = nullptr;   // [bn_cells]
 };
 
 namespace bcu {
@@ -121,5 +165,15 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
                 const uint64_t* d_offset_base = nullptr,  // device u64 added to every offset (chunked joins)
                 const bcu_filter* filter = nullptr, const uint8_t* d_qstrand = nullptr,
                 uint64_t* total_mapped = nullptr);  // device-visible pinned host u64 that also receives the total
+
+// bin layout of a finished index (index_build.cu); `table` = host copy of the [n_comp][n_groups] descriptors
+int build_bin_layout(bcu_index* ix, const GroupDesc* table, cudaStream_t stream);
+// the binned join (binned_join.cu); returns BCU_NOT_TAKEN when the call is not eligible: the caller then runs
+// the general path
+constexpr int BCU_NOT_TAKEN = 1;
+int launch_join_binned(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_qgroup, const uint32_t* d_qlow,
+                       const uint32_t* d_qhigh, uint64_t* d_offsets, uint64_t pair_capacity, uint32_t* d_hit_query,
+                       uint32_t* d_hit_target, uint64_t* d_total, uint32_t query_id_base, cudaStream_t stream,
+                       uint64_t* total_mapped);
 
 }  // namespace bcu

@@ -250,6 +250,10 @@ static void free_index_members(bcu_index* ix) {
   cudaFreeAsync(ix->d_dir, nullptr);
   cudaFreeAsync(ix->d_hs, nullptr);
   cudaFreeAsync(ix->d_dirh, nullptr);
+  cudaFreeAsync(ix->d_low, nullptr);
+  cudaFreeAsync(ix->d_bn_desc, nullptr);
+  cudaFreeAsync(ix->d_bn_groups, nullptr);
+  cudaFreeAsync(ix->d_bn_cell2bin, nullptr);
   cudaGetLastError();
 }
 
@@ -514,6 +518,7 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
   ix->n_groups = n_groups;
   ix->n_comp = n_comp;
   ix->class_base_len = base_len;
+  ix->max_len = max_len;
   ix->max_gval = n_groups ? gval[n_groups - 1] : 0;
   ix->shift = shift;
   ix->shifts = class_shift[0] | (class_shift[1] << 8) | (class_shift[2] << 16) | (class_shift[3] << 24);
@@ -536,6 +541,193 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
   BCU_LAUNCHED();
   BCU_CUDA(cudaStreamSynchronize(stream));  // host vectors are temporaries
   mark("directories");
+  BCU_TRY(build_bin_layout(ix, table.data(), stream));
+  mark("bin layout");
+  return BCU_OK;
+}
+
+// ---- bin layout (binned_join.cu): coordinate tiles of the index that fit one CTA's shared memory ----------
+__global__ void __launch_bounds__(kThreads)
+    split_low_kernel(const uint2* __restrict__ lowhigh, uint64_t n_padded, uint32_t* __restrict__ low) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_padded) low[r] = lowhigh[r].x;
+}
+
+// For every class slot c (blockIdx.y), group g and cell boundary j (0..n_cells_g): the first row of segment (c, g)
+// with low >= j << shift, and the first row with low >= (j << shift) - maxlen_c (the rows that may still reach
+// into the cell). bound_base[g] = first boundary index of group g (n_cells_g + 1 boundaries per group).
+__global__ void __launch_bounds__(kThreads)
+    cell_rows_kernel(const GroupDesc* __restrict__ table, uint32_t n_groups, const uint32_t* __restrict__ bound_base,
+                     uint32_t n_bounds, uint32_t shift, const uint32_t* __restrict__ low, uint4 maxlen4,
+                     uint32_t* __restrict__ start_row, uint32_t* __restrict__ halo_row) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+  if (b >= n_bounds) return;
+  uint32_t lo = 0, hi = n_groups;  // group of boundary b: last g with bound_base[g] <= b
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (bound_base[mid] <= b) lo = mid; else hi = mid;
+  }
+  const GroupDesc seg = table[(size_t)c * n_groups + lo];
+  const uint64_t x = (uint64_t)(b - bound_base[lo]) << shift;
+  const uint32_t maxlen = c == 0 ? maxlen4.x : (c == 1 ? maxlen4.y : (c == 2 ? maxlen4.z : maxlen4.w));
+  const uint64_t xh = x > maxlen ? x - maxlen : 0;
+  auto lower = [&](uint64_t key) {
+    uint32_t a = seg.row_begin, e = seg.row_end;
+    while (a < e) {
+      const uint32_t m = a + ((e - a) >> 1);
+      if ((uint64_t)low[m] < key) a = m + 1; else e = m;
+    }
+    return a;
+  };
+  const bool empty = seg.nb == 0;
+  start_row[(size_t)c * n_bounds + b] = empty ? 0u : lower(x);
+  halo_row[(size_t)c * n_bounds + b] = empty ? 0u : lower(xh);
+}
+
+int build_bin_layout(bcu_index* ix, const GroupDesc* table, cudaStream_t stream) {
+  ix->bn_bins = 0;
+  const char* off = std::getenv("BCU_BINNED");
+  if (ix->n == 0 || ix->n_groups == 0 || (off && off[0] == '0')) return BCU_OK;
+  const uint32_t G = ix->n_groups, C = ix->n_comp;
+  // top non-empty class slot and the length bound of every slot (length_class_kernel: slot c < top holds
+  // lengths < base * 4^c, the top slot everything above)
+  uint32_t top = 0;
+  for (uint32_t c = 0; c < C; ++c)
+    for (uint32_t g = 0; g < G; ++g)
+      if (table[(size_t)c * G + g].nb) top = c;
+  uint32_t maxlen[kBinMaxClasses] = {0, 0, 0, 0};
+  uint64_t rows_c[kBinMaxClasses] = {0, 0, 0, 0};
+  for (uint32_t c = 0; c <= top; ++c) {
+    uint64_t lim = ix->class_base_len;
+    for (uint32_t k = 0; k < c; ++k) lim *= 4;
+    maxlen[c] = (c < top && lim - 1 < ix->max_len) ? (uint32_t)(lim - 1) : ix->max_len;
+    for (uint32_t g = 0; g < G; ++g) rows_c[c] += table[(size_t)c * G + g].row_end - table[(size_t)c * G + g].row_begin;
+  }
+  // coordinate extent of every group (upper bound from the directory sizes), cell width, routing tables
+  std::vector<uint64_t> cmax(G, 0);
+  uint64_t span = 0;
+  for (uint32_t g = 0; g < G; ++g) {
+    for (uint32_t c = 0; c <= top; ++c) {
+      const GroupDesc& d = table[(size_t)c * G + g];
+      if (d.nb) cmax[g] = std::max<uint64_t>(cmax[g], std::min<uint64_t>(((uint64_t)d.nb << d.shift) - 1, 0xffffffffull));
+    }
+    span += cmax[g] + 1;
+  }
+  // a class whose candidate window (rows starting within maxlen of a query) averages more than kWindowMax rows
+  // would overflow the per-query hit masks of the tile probe most of the time: such indexes keep the general path
+  const double kWindowMax = env_double("BCU_BINNED_WINDOW", 16.0);
+  for (uint32_t c = 0; c <= top; ++c)
+    if ((double)rows_c[c] * ((double)maxlen[c] + 1.0) / (double)span > kWindowMax) return BCU_OK;
+  uint32_t shift = 0;
+  for (; shift < 32; ++shift) {
+    uint64_t cells = 0;
+    for (uint32_t g = 0; g < G; ++g) cells += (cmax[g] >> shift) + 1;
+    if (cells <= kBinMaxCells) break;
+  }
+  if (shift >= 32) return BCU_OK;  // more groups than cells: not eligible
+  std::vector<BinGroup> groups(G);
+  std::vector<uint32_t> bound_base(G + 1);
+  uint32_t n_cells = 0;
+  for (uint32_t g = 0; g < G; ++g) {
+    groups[g].gval = table[g].gval;
+    groups[g].cell_base = n_cells;
+    groups[g].n_cells = (uint32_t)((cmax[g] >> shift) + 1);
+    groups[g].pad = 0;
+    bound_base[g] = n_cells + g;
+    n_cells += groups[g].n_cells;
+  }
+  bound_base[G] = n_cells + G;
+  const uint32_t n_bounds = n_cells + G;
+
+  TempBuffers tmp(stream);
+  uint32_t *d_bound_base, *d_start, *d_halo;
+  BCU_CUDA(tmp.alloc(&d_bound_base, G + 1));
+  BCU_CUDA(tmp.alloc(&d_start, (uint64_t)C * n_bounds));
+  BCU_CUDA(tmp.alloc(&d_halo, (uint64_t)C * n_bounds));
+  BCU_CUDA(cudaMallocAsync((void**)&ix->d_low, (ix->n + 4) * 4, stream));
+  ix->bytes += ix->n * 4;
+  split_low_kernel<<<(unsigned)((ix->n + 4 + kThreads - 1) / kThreads), kThreads, 0, stream>>>(ix->d_lowhigh, ix->n + 4,
+                                                                                           ix->d_low);
+  BCU_LAUNCHED();
+  BCU_CUDA(cudaMemcpyAsync(d_bound_base, bound_base.data(), (G + 1) * 4, cudaMemcpyHostToDevice, stream));
+  cell_rows_kernel<<<dim3((n_bounds + kThreads - 1) / kThreads, C), kThreads, 0, stream>>>(
+      ix->d_groups, G, d_bound_base, n_bounds, shift, ix->d_low, make_uint4(maxlen[0], maxlen[1], maxlen[2], maxlen[3]),
+      d_start, d_halo);
+  BCU_LAUNCHED();
+  std::vector<uint32_t> start((size_t)C * n_bounds), halo((size_t)C * n_bounds);
+  BCU_CUDA(cudaMemcpyAsync(start.data(), d_start, start.size() * 4, cudaMemcpyDeviceToHost, stream));
+  BCU_CUDA(cudaMemcpyAsync(halo.data(), d_halo, halo.size() * 4, cudaMemcpyDeviceToHost, stream));
+  BCU_CUDA(cudaStreamSynchronize(stream));
+
+  // greedy: extend a bin cell by cell while its rows (all classes, with their halos and the 4-row alignment
+  // of the bulk copies) fit the tile
+  const uint32_t rows_cap = (uint32_t)std::min<double>(kBinRowsCap, env_double("BCU_BIN_ROWS", kBinRowsCap));
+  auto tile_rows = [&](uint32_t g, uint32_t j0, uint32_t j1) {
+    uint64_t rows = 0;
+    for (uint32_t c = 0; c <= top; ++c) {
+      const uint32_t h = halo[(size_t)c * n_bounds + bound_base[g] + j0], e = start[(size_t)c * n_bounds + bound_base[g] + j1];
+      if (e > h) rows += (uint64_t)(e - (h & ~3u) + 3) / 4 * 4;
+    }
+    return rows;
+  };
+  std::vector<BinDesc> bins;
+  std::vector<uint16_t> cell2bin(n_cells, (uint16_t)kBinNull);
+  for (uint32_t g = 0; g < G; ++g) {
+    const uint32_t nc = groups[g].n_cells;
+    for (uint32_t j0 = 0; j0 < nc;) {
+      uint32_t j1 = j0 + 1;
+      if (tile_rows(g, j0, j1) > rows_cap) return BCU_OK;  // one cell does not fit: not eligible
+      while (j1 < nc && tile_rows(g, j0, j1 + 1) <= rows_cap) ++j1;
+      if (bins.size() >= kBinMaxBins) return BCU_OK;
+      BinDesc b;
+      std::memset(&b, 0, sizeof(b));
+      b.group = g;
+      b.x_begin = (uint32_t)((uint64_t)j0 << shift);
+      const bool last = j1 == nc;
+      b.x_end = last ? 0u : (uint32_t)((uint64_t)j1 << shift);
+      const uint64_t x_end_eff = last ? cmax[g] + 1 : ((uint64_t)j1 << shift);
+      uint32_t s_off = 0, lut_off = 0;
+      for (uint32_t c = 0; c <= top; ++c) {
+        BinClass& k = b.cls[c];
+        const uint32_t h = halo[(size_t)c * n_bounds + bound_base[g] + j0], e = start[(size_t)c * n_bounds + bound_base[g] + j1];
+        k.maxlen = maxlen[c];
+        k.x0 = b.x_begin > maxlen[c] ? b.x_begin - maxlen[c] : 0u;
+        k.s_off = s_off;
+        k.lut_off = lut_off;
+        if (e > h) {
+          k.row0 = h & ~3u;
+          k.n_copy = (e - k.row0 + 3) / 4 * 4;
+          k.lo = h - k.row0;
+          k.hi = e - k.row0;
+        }
+        const uint64_t spanc = x_end_eff - k.x0;  // >= 1
+        const uint64_t budget = std::max<uint64_t>(16, (uint64_t)(k.hi - k.lo) * 3 / 4);
+        uint32_t ls = 0;
+        while (((spanc - 1) >> ls) + 1 > budget) ++ls;
+        k.ls = ls;
+        k.nsub = (uint32_t)(((spanc - 1) >> ls) + 1);
+        s_off += k.n_copy;
+        lut_off += k.nsub + 1;
+      }
+      if (s_off > kBinRowsCap || lut_off > kBinLutCap) return BCU_OK;
+      b.n_rows = s_off;
+      for (uint32_t j = j0; j < j1; ++j) cell2bin[groups[g].cell_base + j] = (uint16_t)bins.size();
+      bins.push_back(b);
+      j0 = j1;
+    }
+  }
+  if (bins.empty()) return BCU_OK;
+  BCU_CUDA(cudaMallocAsync((void**)&ix->d_bn_desc, bins.size() * sizeof(BinDesc), stream));
+  BCU_CUDA(cudaMallocAsync((void**)&ix->d_bn_groups, (size_t)G * sizeof(BinGroup), stream));
+  BCU_CUDA(cudaMallocAsync((void**)&ix->d_bn_cell2bin, (size_t)n_cells * 2, stream));
+  BCU_CUDA(cudaMemcpyAsync(ix->d_bn_desc, bins.data(), bins.size() * sizeof(BinDesc), cudaMemcpyHostToDevice, stream));
+  BCU_CUDA(cudaMemcpyAsync(ix->d_bn_groups, groups.data(), (size_t)G * sizeof(BinGroup), cudaMemcpyHostToDevice, stream));
+  BCU_CUDA(cudaMemcpyAsync(ix->d_bn_cell2bin, cell2bin.data(), (size_t)n_cells * 2, cudaMemcpyHostToDevice, stream));
+  BCU_CUDA(cudaStreamSynchronize(stream));  // host vectors are temporaries
+  ix->bytes += bins.size() * sizeof(BinDesc) + (size_t)G * sizeof(BinGroup) + (size_t)n_cells * 2;
+  ix->bn_bins = (uint32_t)bins.size();
+  ix->bn_cells = n_cells;
+  ix->bn_cell_shift = shift;
   return BCU_OK;
 }
 
@@ -610,7 +802,7 @@ constexpr uint64_t kImageAlign = 256;
 enum { kImgLowHigh, kImgHigh, kImgId, kImgHs, kImgGroups, kImgDir, kImgDirh, kImgArrays };
 struct ImageHeader {
   uint64_t magic, total_bytes, n, n_bins, bytes;
-  uint32_t n_groups, n_comp, class_base_len, shift, max_gval, sort_passes, shifts, reserved;
+  uint32_t n_groups, n_comp, class_base_len, shift, max_gval, sort_passes, shifts, max_len;
   uint64_t offset[kImgArrays], size[kImgArrays];
   uint8_t pad[256 - 5 * 8 - 8 * 4 - 2 * 8 * kImgArrays];
 };
@@ -622,6 +814,7 @@ void image_layout(const bcu_index* ix, ImageHeader* h) {
   h->n = ix->n; h->n_bins = ix->n_bins; h->bytes = ix->bytes;
   h->n_groups = ix->n_groups; h->n_comp = ix->n_comp; h->class_base_len = ix->class_base_len;
   h->shift = ix->shift; h->max_gval = ix->max_gval; h->sort_passes = ix->sort_passes; h->shifts = ix->shifts;
+  h->max_len = ix->max_len;
   const uint64_t rows = ix->n ? ix->n + 4 : 0;  // the padded row arrays travel with their padding
   h->size[kImgLowHigh] = rows * sizeof(uint2);
   h->size[kImgHigh] = h->size[kImgId] = h->size[kImgHs] = rows * 4;
@@ -701,6 +894,7 @@ extern "C" int bcu_index_import_dev(int device, const void* d_image, uint64_t by
   ix->n = h.n; ix->n_bins = h.n_bins; ix->bytes = h.bytes;
   ix->n_groups = h.n_groups; ix->n_comp = h.n_comp; ix->class_base_len = h.class_base_len;
   ix->shift = h.shift; ix->max_gval = h.max_gval; ix->sort_passes = h.sort_passes; ix->shifts = h.shifts;
+  ix->max_len = h.max_len;
   keep_pool_warm(device);
   void* slot[kImgArrays];
   image_slots(ix, slot);
@@ -719,6 +913,19 @@ extern "C" int bcu_index_import_dev(int device, const void* d_image, uint64_t by
     free_index_members(ix);
     delete ix;
     return rc;
+  }
+  if (ix->n) {  // the bin layout is derived data: rebuilt from the imported arrays rather than shipped
+    std::vector<GroupDesc> table((size_t)ix->n_comp * ix->n_groups);
+    const uint64_t bytes_before = ix->bytes;
+    if (cudaMemcpyAsync(table.data(), ix->d_groups, table.size() * sizeof(GroupDesc), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+        cudaStreamSynchronize(stream) != cudaSuccess) rc = BCU_E_CUDA;
+    if (rc == BCU_OK) rc = build_bin_layout(ix, table.data(), stream);
+    ix->bytes = bytes_before;  // `bytes` travels in the header and already counts the exporter's layout
+    if (rc != BCU_OK) {
+      free_index_members(ix);
+      delete ix;
+      return rc;
+    }
   }
   *out = ix;
   return BCU_OK;
@@ -740,6 +947,6 @@ extern "C" int bcu_index_get_info(const bcu_index* ix, bcu_index_info* info) {
   info->n_bins = ix->n_bins;
   info->device_bytes = ix->bytes;
   info->device = ix->device;
-  info->reserved = 0;
+  info->binned_tiles = (int32_t)ix->bn_bins;
   return BCU_OK;
 }

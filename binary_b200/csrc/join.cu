@@ -1120,6 +1120,12 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
     if (mode == kModeAny && n_q) BCU_CUDA(cudaMemsetAsync(d_any, 0, n_q, stream));
     return BCU_OK;
   }
+  if (!d_offset_base && !(filter && filter->kind != BCU_FILTER_NONE)) {
+    // large batches against an index beyond L2 take the binned path (binned_join.cu) when the index has a bin layout
+    const int rc = launch_join_binned(ix, mode, n_q, d_qgroup, d_qlow, d_qhigh, d_offsets, pair_capacity, d_hit_query,
+                                      d_hit_target, d_total, query_id_base, stream, total_mapped);
+    if (rc != BCU_NOT_TAKEN) return rc;
+  }
   JoinArgs a;
   a.lowhigh = ix->d_lowhigh;
   a.high = ix->d_high;

@@ -62,7 +62,8 @@ typedef struct bcu_index_info {
   uint64_t n_bins;       /* directory entries over all groups/components                     */
   uint64_t device_bytes; /* device memory held by the index                                  */
   int32_t device;
-  int32_t reserved;
+  int32_t binned_tiles;  /* shared-memory sized coordinate tiles of the index (0 = no bin layout: large batches
+                            take the general path too); see bcu_join_dev */
 } bcu_index_info;
 
 /* Optional pair filter, evaluated on the device on top of the overlap predicate so that rejected pairs are
@@ -140,9 +141,13 @@ int bcu_query_scatter_dev(const bcu_index* index, uint64_t n_q, const uint32_t* 
                           const uint64_t* d_offsets, uint32_t* d_hit_query, uint32_t* d_hit_target,
                           void* stream);
 /* Count + prefix sum + scatter (probe and emit kernels back to back). d_total: u64[1] on device,
- * receives the number of pairs the join has (also when it exceeds pair_capacity, in which case pairs
- * beyond the capacity are not written). query_id_base is added to every emitted query id (sharding).
- * d_hit_query may be NULL (column not produced). */
+ * receives the number of pairs the join has (also when it exceeds pair_capacity, in which case nothing
+ * is written at or beyond the capacity, offsets and total are complete, and the pairs below the capacity
+ * are complete only on the general path -- treat them as unspecified and retry with a larger buffer).
+ * query_id_base is added to every emitted query id (sharding). d_hit_query may be NULL (column not produced).
+ * Large batches (>= 2 Mi queries) against an index with a bin layout that exceeds L2 are answered by the
+ * binned path (queries routed to shared-memory sized tiles of the index; binned_join.cu); the result is the
+ * same CSR. BCU_BINNED=0 / =1 in the environment disables / forces that path. */
 int bcu_join_dev(const bcu_index* index, uint64_t n_q, const uint32_t* d_qgroup,
                  const uint32_t* d_qlow, const uint32_t* d_qhigh, uint64_t* d_offsets,
                  uint64_t pair_capacity, uint32_t* d_hit_query, uint32_t* d_hit_target,
