@@ -55,6 +55,7 @@ SIGNATURES = {
     "bcu_query_scatter": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp, vp, vp]),
     "bcu_join": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp, C.c_uint64, vp, vp, u64p]),
     "bcu_trim": (C.c_int, []),
+    "bcu_join_multi": (C.c_int, [C.POINTER(vp), C.c_int, C.c_uint64, vp, vp, vp, vp, vp, C.c_uint64, vp, vp, u64p]),
     "bcu_join_filtered": (C.c_int, [vp, vp, C.c_uint64, vp, vp, vp, vp, vp, C.c_uint64, vp, vp, u64p]),
     "bcu_join_filtered_dev": (C.c_int, [vp, vp, C.c_uint64, vp, vp, vp, vp, vp, C.c_uint64, vp, vp, vp, C.c_uint32, vp]),
     "bcu_query_any": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp]),

@@ -37,13 +37,13 @@ namespace bcu {
 constexpr int kTileQ = 4096;          // queries per routing tile
 constexpr int kSortThreads = 512;
 constexpr int kSortQPT = kTileQ / kSortThreads;
-constexpr int kProbeThreads = 512;
+constexpr int kProbeThreads = 1024;
 constexpr int kProbeWarps = kProbeThreads / 32;
-constexpr int kStageIds = 512;        // hits staged per warp and round
+constexpr int kStageIds = 256;        // hits staged per warp and round
 constexpr uint32_t kSlabIds = 8192;   // staging is reserved per warp in slabs: one global atomic per ~40 rounds
 constexpr int kPlaceThreads = 512;
 constexpr int kPlaceQPT = kTileQ / kPlaceThreads;
-constexpr int kPlaceCap = 32768;      // target ids assembled per tile and round
+constexpr int kPlaceCap = 16384;      // target ids assembled per tile and round
 constexpr uint32_t kMaskRows = 32;    // candidate window a lane can record (one hit-mask word per class)
 constexpr int kBnDirectGroups = 1024; // group values below this are routed through a direct map
 constexpr uint32_t kNotStored = 0xffffffffu;  // sres.x of a hit list that did not fit the staging area (the join
@@ -51,10 +51,12 @@ constexpr uint32_t kNotStored = 0xffffffffu;  // sres.x of a hit list that did n
 
 struct BinnedArgs {
   // index
-  const uint32_t* __restrict__ low;
+  const uint32_t* __restrict__ low;   // (group, low)-sorted columns the bins' own rows are copied from
   const uint32_t* __restrict__ high;
   const uint32_t* __restrict__ ids;
-  const uint2* __restrict__ lowhigh;
+  const unsigned char* __restrict__ blob;  // per bin: sub_start | cov_rel | cov_high | cov_id
+  const uint2* __restrict__ lowhigh;  // general index (spill path)
+  const uint32_t* __restrict__ gids;
   const DirEntry* __restrict__ dir;
   const GroupDesc* __restrict__ gtable;  // [n_cls][n_groups] (general index: used by the spill path)
   const BinDesc* __restrict__ desc;
@@ -89,6 +91,7 @@ struct BinnedArgs {
   uint64_t* total_mapped;
   uint32_t qid_base;
   int emit;          // 0 = offsets only (count mode)
+  int ht_aligned;    // hit_target is 16-byte aligned (vector stores)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -142,19 +145,30 @@ __device__ __forceinline__ int run_owner(uint32_t incl, uint32_t f) {
 
 // ---------------------------------------------------------------------------------------------------
 // Routing: tile-local counting sort by bin. Persistent CTAs (the routing tables are staged once per CTA).
-// Dynamic shared memory: hist[n_bins + 2] u32 | rec[kTileQ] uint2 | loc[kTileQ] u16 | cell2bin[n_cells] u16 |
-// groups[n_groups] BinGroup | gmap[kBnDirectGroups] u16
-__global__ void __launch_bounds__(kSortThreads) bin_sort_kernel(const BinnedArgs a) {
+// Ranks come from per-warp histograms updated WITHOUT atomics: the lanes of a warp that hold the same bin find
+// each other with match.any, the first of them adds the group's size to the warp's
+// counter (shared-memory atomics cost ~2 cycles per LANE on this machine: 4096 of them per tile were 80 % of
+// this kernel's time). With more than kSortMaxWarpHistBins bins the per-warp histograms do not fit and
+// shared-memory atomics are used instead.
+// Dynamic shared memory: rec[kTileQ] uint2 | hist[K + 2] u32 | groups[n_groups] BinGroup | loc[kTileQ] u16 |
+// cell2bin[n_cells] u16 | gmap[kBnDirectGroups] u16 | whist[kSortWarps][K + 2] u16 (WARP_HIST only)
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr uint32_t kSortMaxWarpHistBins = 2046;
+
+template <bool WARP_HIST>
+__global__ void __launch_bounds__(kSortThreads, 2) bin_sort_kernel(const BinnedArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t K = a.n_bins;
+  const uint32_t Kp = (K + 2 + 3) & ~3u;
   uint2* s_rec = reinterpret_cast<uint2*>(smem_raw);
   uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_rec + kTileQ);
-  BinGroup* s_grp = reinterpret_cast<BinGroup*>(s_hist + ((K + 2 + 3) & ~3u));
+  BinGroup* s_grp = reinterpret_cast<BinGroup*>(s_hist + Kp);
   uint16_t* s_loc = reinterpret_cast<uint16_t*>(s_grp + a.n_groups);
   uint16_t* s_c2b = s_loc + kTileQ;
   uint16_t* s_gmap = s_c2b + ((a.n_cells + 7) & ~7u);
+  uint16_t* s_whist = s_gmap + kBnDirectGroups;  // [kSortWarps][Kp]
   __shared__ uint64_t s_scan[kSortThreads / 32 + 1];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool direct = a.max_gval < (uint32_t)kBnDirectGroups;
 
   for (uint32_t i = tid; i < a.n_cells; i += kSortThreads) s_c2b[i] = a.cell2bin[i];
@@ -167,19 +181,31 @@ __global__ void __launch_bounds__(kSortThreads) bin_sort_kernel(const BinnedArgs
 
   for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     __syncthreads();  // previous tile's copy-out is done; the group map is visible
-    for (uint32_t i = tid; i < K + 2; i += kSortThreads) s_hist[i] = 0;
+    if (WARP_HIST) {
+      uint32_t* w32 = reinterpret_cast<uint32_t*>(s_whist);
+      for (uint32_t i = tid; i < kSortWarps * Kp / 2; i += kSortThreads) w32[i] = 0;
+    } else {
+      for (uint32_t i = tid; i < K + 2; i += kSortThreads) s_hist[i] = 0;
+    }
     __syncthreads();
     const uint64_t q0 = (uint64_t)tile * kTileQ;
-    uint32_t ql[kSortQPT], qh[kSortQPT], bin[kSortQPT], rank[kSortQPT];
+    uint32_t ql[kSortQPT], qh[kSortQPT], qg[kSortQPT], bin[kSortQPT], rank[kSortQPT];
+#pragma unroll
+    for (int j = 0; j < kSortQPT; ++j) {  // all the loads of the tile first
+      const uint64_t q = q0 + (uint32_t)(j * kSortThreads + tid);
+      ql[j] = qh[j] = qg[j] = 0;
+      if (q < a.n_q) {
+        ql[j] = a.qlow[q];
+        qh[j] = a.qhigh[q];
+        if (a.qgroup) qg[j] = a.qgroup[q];
+      }
+    }
 #pragma unroll
     for (int j = 0; j < kSortQPT; ++j) {
       const uint64_t q = q0 + (uint32_t)(j * kSortThreads + tid);
       bin[j] = K + 1;  // K = known query without a bin, K + 1 = past the end of the batch
-      ql[j] = qh[j] = 0;
       if (q < a.n_q) {
-        ql[j] = a.qlow[q];
-        qh[j] = a.qhigh[q];
-        const uint32_t g = a.qgroup ? a.qgroup[q] : 0u;
+        const uint32_t g = qg[j];
         uint32_t gi = 0xffffu;
         if (direct) {
           if (g < (uint32_t)kBnDirectGroups) gi = s_gmap[g];
@@ -200,9 +226,32 @@ __global__ void __launch_bounds__(kSortThreads) bin_sort_kernel(const BinnedArgs
           }
         }
       }
-      rank[j] = bin[j] <= K ? atomicAdd(&s_hist[bin[j]], 1u) : 0u;
+      if (WARP_HIST) {
+        const unsigned peers = __match_any_sync(0xffffffffu, bin[j]);  // lanes of this warp holding the same bin
+        const uint32_t before = __popc(peers & ((1u << lane) - 1u));
+        uint16_t* cnt = s_whist + warp * Kp + bin[j];
+        const uint32_t h = *cnt;
+        __syncwarp();
+        if (before == 0) *cnt = (uint16_t)(h + __popc(peers));
+        __syncwarp();
+        rank[j] = h + before;
+      } else {
+        rank[j] = bin[j] <= K ? atomicAdd(&s_hist[bin[j]], 1u) : 0u;
+      }
     }
     __syncthreads();
+    if (WARP_HIST)  // per bin: counts of the warps -> exclusive prefix over the warps, total into hist
+      for (uint32_t b = tid; b < K + 2; b += kSortThreads) {
+        uint32_t e = 0;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) {
+          const uint32_t t = s_whist[w * Kp + b];
+          s_whist[w * Kp + b] = (uint16_t)e;
+          e += t;
+        }
+        s_hist[b] = e;
+      }
+    if (WARP_HIST) __syncthreads();
     // exclusive scan of the K + 1 counters (contiguous pieces per thread), in place
     const uint32_t per = (K + 1 + kSortThreads - 1) / kSortThreads;
     const uint32_t b0 = min((uint32_t)tid * per, K + 1), b1 = min(b0 + per, K + 1);
@@ -215,6 +264,7 @@ __global__ void __launch_bounds__(kSortThreads) bin_sort_kernel(const BinnedArgs
       s_hist[b] = (uint32_t)run;
       run += c;
     }
+    __syncthreads();
     if (tid == 0) s_hist[K + 1] = (uint32_t)total;  // queries of the tile
     __syncthreads();
     uint16_t* trun = a.trun + (uint64_t)tile * (K + 2);
@@ -222,7 +272,7 @@ __global__ void __launch_bounds__(kSortThreads) bin_sort_kernel(const BinnedArgs
 #pragma unroll
     for (int j = 0; j < kSortQPT; ++j)
       if (bin[j] <= K) {
-        const uint32_t slot = s_hist[bin[j]] + rank[j];
+        const uint32_t slot = s_hist[bin[j]] + rank[j] + (WARP_HIST ? (uint32_t)s_whist[warp * Kp + bin[j]] : 0u);
         s_rec[slot] = make_uint2(ql[j], qh[j]);
         s_loc[slot] = (uint16_t)(j * kSortThreads + tid);
       }
@@ -259,30 +309,86 @@ __global__ void __launch_bounds__(256) bin_transpose_kernel(const BinnedArgs a) 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// The tile probe. Dynamic shared memory: low[kBinRowsCap] | high[kBinRowsCap] | id[kBinRowsCap] (u32) |
-// stage[kProbeWarps][kStageIds] u32 | lut[kBinLutCap] u16
-struct ProbeHit {
-  uint32_t mask[kBinMaxClasses];  // bit j = row lb + j of the class's window is a hit
-  uint32_t lb[kBinMaxClasses];    // tile-relative first row of the window (already offset by the class's s_off)
-};
+// The tile probe. Dynamic shared memory: tile[kBinTileBytes] (own rows low | high | id, then the bin's blob:
+// sub_start | cov_rel | cov_high | cov_id) | stage[kProbeWarps][kStageIds] u32.
+// One CTA per SM (the tile fills its shared memory), so latency is hidden by the warps of that one CTA and by
+// instruction-level parallelism inside a lane: candidate rows are tested four at a time, staged ids are fetched
+// four at a time, and the queries of the step after next are brought into L2 (prefetch.global.L2) while the
+// current step is being answered. Round 2 profile of the first version (length classes + max-length windows):
+// issue-bound at 49 warp instructions per query, 58 % of them in the window test and the hit expansion -- hence
+// the coverage lists (common.cuh): ~1.5 candidates per hit instead of 2.9 and no per-class work.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Shared memory through 32-bit shared-window addresses: with the kernel at its register cap the compiler
+// otherwise rebuilds the generic base of the dynamic array before every access (4 extra instructions per load
+// or store in the round-2 profile). The tile is read-only while a bin is being answered (plain asm, may be
+// scheduled freely); the staging rows are written and read back by the same warp (volatile).
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t addr) {
+  uint16_t v;
+  asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32_volatile(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// hit mask of the w <= 32 candidates whose `high` values start at shared address `addr`: bit j = (high[j] >= ql)
+__device__ __forceinline__ uint32_t window_mask(uint32_t addr, uint32_t w, uint32_t ql) {
+  uint32_t mask = 0;
+  uint32_t j = 0;
+  for (; j + 2 <= w; j += 2) {  // two loads in flight
+    const uint32_t v0 = lds32(addr + 4u * j), v1 = lds32(addr + 4u * j + 4u);
+    mask |= ((uint32_t)(v0 >= ql) | ((uint32_t)(v1 >= ql) << 1)) << j;
+  }
+  if (j < w) mask |= (uint32_t)(lds32(addr + 4u * j) >= ql) << j;
+  return mask;
+}
+
+// the ids of the hits in `mask` (candidate j -> shared word ids + 4j) are appended at shared address `out`
+__device__ __forceinline__ uint32_t expand_hits(uint32_t mask, uint32_t ids, uint32_t out) {
+  while (mask) {
+    const uint32_t j = (uint32_t)__ffs(mask) - 1u;
+    mask &= mask - 1u;
+    sts32(out, lds32(ids + 4u * j));
+    out += 4u;
+  }
+  return out;
+}
+// the same for a warp whose hits exceed the staging row: only positions [0, kStageIds) of the round are kept
+__device__ __forceinline__ uint32_t expand_hits_clipped(uint32_t mask, uint32_t ids, uint32_t stage, uint32_t p) {
+  while (mask) {
+    const uint32_t j = (uint32_t)__ffs(mask) - 1u;
+    mask &= mask - 1u;
+    if (p < (uint32_t)kStageIds) sts32(stage + 4u * p, lds32(ids + 4u * j));  // p wraps far above for earlier hits
+    ++p;
+  }
+  return p;
+}
 
 template <bool EMIT>
 __global__ void __launch_bounds__(kProbeThreads, 1) bin_probe_kernel(const BinnedArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t* s_low = reinterpret_cast<uint32_t*>(smem_raw);
-  uint32_t* s_high = s_low + kBinRowsCap;
-  uint32_t* s_id = s_high + kBinRowsCap;
-  uint32_t* s_stage = s_id + kBinRowsCap;
-  uint16_t* s_lut = reinterpret_cast<uint16_t*>(s_stage + kProbeWarps * kStageIds);
   __shared__ BinDesc s_desc;
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t s_unit;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint32_t* const my_stage = s_stage + warp * kStageIds;
+  const uint32_t sm = smem_u32(smem_raw);
+  const uint32_t a_stage = sm + kBinTileBytes + (uint32_t)warp * kStageIds * 4u;  // this warp's staging row
   if (tid == 0) mbar_init(&s_bar, 1);
   __syncthreads();
   uint32_t parity = 0;
   uint64_t slab_cur = 0, slab_end = 0;  // this warp's reserved piece of the staging area (warp-uniform)
+  constexpr uint32_t kStride = kProbeWarps * 32;  // tiles between two steps of one warp
 
   for (;;) {
     __syncthreads();  // every warp is done with the previous bin's tile
@@ -293,42 +399,36 @@ __global__ void __launch_bounds__(kProbeThreads, 1) bin_probe_kernel(const Binne
     for (uint32_t i = tid; i < sizeof(BinDesc) / 4; i += kProbeThreads)
       reinterpret_cast<uint32_t*>(&s_desc)[i] = reinterpret_cast<const uint32_t*>(a.desc + k)[i];
     __syncthreads();
+    const uint32_t n_copy = s_desc.n_copy, nsub = s_desc.nsub, n_cov = s_desc.n_cov;
+    const uint32_t tab = ((nsub + 1 + 7) & ~7u) * 2u;  // bytes of one u16 table
+    // shared addresses of the tile's pieces: own rows low | high | id, then the blob sub_start | cov_rel | cov_high | cov_id
+    const uint32_t a_low = sm, a_high = sm + 4u * n_copy, a_id = sm + 8u * n_copy, a_sub = sm + 12u * n_copy;
+    const uint32_t a_rel = a_sub + tab, a_chigh = a_rel + tab, a_cid = a_chigh + 4u * n_cov;
     if (tid == 0) {  // one thread arms the barrier with the byte count and issues the bulk copies
-      mbar_expect_tx(&s_bar, s_desc.n_rows * 12u);
-      for (uint32_t c = 0; c < a.n_cls; ++c) {
-        const BinClass& kc = s_desc.cls[c];
-        if (kc.n_copy == 0) continue;
-        bulk_g2s(s_low + kc.s_off, a.low + kc.row0, kc.n_copy * 4u, &s_bar);
-        bulk_g2s(s_high + kc.s_off, a.high + kc.row0, kc.n_copy * 4u, &s_bar);
-        bulk_g2s(s_id + kc.s_off, a.ids + kc.row0, kc.n_copy * 4u, &s_bar);
+      mbar_expect_tx(&s_bar, n_copy * 12u + s_desc.blob_bytes);
+      if (n_copy) {
+        bulk_g2s(smem_raw, a.low + s_desc.row0, n_copy * 4u, &s_bar);
+        bulk_g2s(smem_raw + 4u * n_copy, a.high + s_desc.row0, n_copy * 4u, &s_bar);
+        bulk_g2s(smem_raw + 8u * n_copy, a.ids + s_desc.row0, n_copy * 4u, &s_bar);
       }
+      bulk_g2s(smem_raw + 12u * n_copy, a.blob + s_desc.blob, s_desc.blob_bytes, &s_bar);
     }
+    // while the tile is on its way: this warp's first two run descriptors (and the L2 prefetch of their queries)
+    const uint32_t* const runs = a.brun + (uint64_t)k * a.n_tiles;
+    uint32_t t0 = warp * 32;
+    uint32_t d0 = (t0 + lane < a.n_tiles) ? runs[t0 + lane] : 0u;
+    uint32_t d1 = (t0 + kStride + lane < a.n_tiles) ? runs[t0 + kStride + lane] : 0u;
+    if (d0 >> 16) prefetch_l2(a.brec + (uint64_t)(t0 + lane) * kTileQ + (d0 & 0xffffu));
+    if (d1 >> 16) prefetch_l2(a.brec + (uint64_t)(t0 + kStride + lane) * kTileQ + (d1 & 0xffffu));
     mbar_wait(&s_bar, parity);
     parity ^= 1u;
-    // sub-cell tables: lut[j] = first row of the class (tile-relative, in [lo, hi]) with low >= x0 + (j << ls)
-    for (uint32_t c = 0; c < a.n_cls; ++c) {
-      const BinClass kc = s_desc.cls[c];
-      uint16_t* lut = s_lut + kc.lut_off;
-      if (kc.hi <= kc.lo) {
-        for (uint32_t j = tid; j <= kc.nsub; j += kProbeThreads) lut[j] = (uint16_t)kc.lo;
-        continue;
-      }
-      for (uint32_t r = kc.lo + tid; r < kc.hi; r += kProbeThreads) {
-        const uint32_t cell = (s_low[kc.s_off + r] - kc.x0) >> kc.ls;               // < nsub
-        const int64_t prev = r > kc.lo ? (int64_t)((s_low[kc.s_off + r - 1] - kc.x0) >> kc.ls) : -1;
-        for (int64_t j = prev + 1; j <= (int64_t)cell; ++j) lut[j] = (uint16_t)r;
-        if (r == kc.hi - 1)
-          for (uint32_t j = cell + 1; j <= kc.nsub; ++j) lut[j] = (uint16_t)kc.hi;
-      }
-    }
-    __syncthreads();
 
-    const uint32_t x_end = s_desc.x_end;
-    const uint32_t* const runs = a.brun + (uint64_t)k * a.n_tiles;
-    for (uint32_t t0 = warp * 32; t0 < a.n_tiles; t0 += kProbeWarps * 32) {  // 32 tiles' runs of this bin per warp step
-      const uint32_t t = t0 + lane;
-      const uint32_t run = t < a.n_tiles ? runs[t] : 0u;
-      const uint32_t r_start = run & 0xffffu, r_n = run >> 16;
+    const uint32_t x_begin = s_desc.x_begin, x_end = s_desc.x_end, ls = s_desc.ls;
+    for (; t0 < a.n_tiles; t0 += kStride) {  // 32 tiles' runs of this bin per warp step
+      // two steps ahead: the run descriptors (a plain load, consumed at the end of this step)
+      const uint32_t t2 = t0 + 2 * kStride + lane;
+      const uint32_t d2 = t2 < a.n_tiles ? runs[t2] : 0u;
+      const uint32_t r_start = d0 & 0xffffu, r_n = d0 >> 16;
       const uint32_t r_incl = warp_incl_scan(r_n, lane);
       const uint32_t m = __shfl_sync(0xffffffffu, r_incl, 31);
       for (uint32_t base = 0; base < m; base += 32) {
@@ -338,45 +438,28 @@ __global__ void __launch_bounds__(kProbeThreads, 1) bin_probe_kernel(const Binne
         const uint32_t o_incl = __shfl_sync(0xffffffffu, r_incl, src), o_n = __shfl_sync(0xffffffffu, r_n, src);
         const uint32_t o_start = __shfl_sync(0xffffffffu, r_start, src);
         const uint64_t slot = (uint64_t)(t0 + src) * kTileQ + o_start + (f - (o_incl - o_n));
-        uint2 q = make_uint2(0, 0);
+        uint2 q = make_uint2(x_begin, x_begin);
         if (valid) q = a.brec[slot];
         const uint32_t ql = q.x, qh = q.y;
 
-        ProbeHit h;
-        uint32_t cnt = 0;
-        bool spill = valid && x_end != 0 && qh >= x_end && qh >= ql;  // reaches past the bin: rows beyond the tile
-#pragma unroll
-        for (uint32_t c = 0; c < kBinMaxClasses; ++c) {
-          h.mask[c] = 0;
-          h.lb[c] = 0;
-          if (c >= a.n_cls || !valid || spill) continue;
-          const BinClass& kc = s_desc.cls[c];
-          if (kc.hi <= kc.lo || qh < kc.x0) continue;  // every row of the tile starts at or after x0
-          const uint32_t* low = s_low + kc.s_off;
-          const uint16_t* lut = s_lut + kc.lut_off;
-          uint32_t ub = lut[min((qh - kc.x0) >> kc.ls, kc.nsub - 1u) + 1u];
-          while (ub > kc.lo && low[ub - 1] > qh) --ub;            // first row with low > q.high
-          const uint32_t lob = ql > kc.maxlen ? ql - kc.maxlen : 0u;  // rows starting before it cannot reach q.low
-          uint32_t lb = kc.lo;
-          if (lob > kc.x0) {
-            lb = lut[min((lob - kc.x0) >> kc.ls, kc.nsub - 1u)];
-            while (lb < ub && low[lb] < lob) ++lb;
-          }
-          const uint32_t w = ub > lb ? ub - lb : 0u;
-          if (w > kMaskRows) { spill = true; continue; }
-          const uint32_t* high = s_high + kc.s_off + lb;
-          uint32_t mask = 0;
-          for (uint32_t j = 0; j < w; ++j) mask |= (uint32_t)(high[j] >= ql) << j;
-          h.mask[c] = mask;
-          h.lb[c] = kc.s_off + lb;
-          cnt += __popc(mask);
+        // candidates: the coverage list of q.low's sub-cell + the own rows from that sub-cell's start up to q.high
+        const uint32_t g = (ql - x_begin) >> ls;  // < nsub: the query was routed here by q.low
+        const uint32_t c0 = lds16(a_rel + 2u * g), wa = lds16(a_rel + 2u * g + 2u) - c0;
+        const uint32_t sa = lds16(a_sub + 2u * g);
+        uint32_t ub = lds16(a_sub + 2u * min((max(qh, ql) - x_begin) >> ls, nsub - 1u) + 2u);
+        while (ub > sa && lds32(a_low + 4u * ub - 4u) > qh) --ub;  // back over the own rows that start beyond q.high
+        const uint32_t wb = ub > sa ? ub - sa : 0u;
+        // the general index answers: inverted queries, queries that reach past the bin, windows beyond the mask
+        const bool spill = valid && (qh < ql || (x_end != 0 && qh >= x_end) || wa > kMaskRows || wb > kMaskRows);
+        uint32_t mask_a = 0, mask_b = 0;
+        if (valid && !spill) {
+          mask_a = window_mask(a_chigh + 4u * c0, wa, ql);
+          mask_b = window_mask(a_high + 4u * sa, wb, ql);
         }
+        const uint32_t cnt = __popc(mask_a) + __popc(mask_b);
         if (spill) {
-          cnt = 0;
-#pragma unroll
-          for (uint32_t c = 0; c < kBinMaxClasses; ++c) h.mask[c] = 0;
           const uint32_t at = atomicAdd(a.n_spill, 1u);
-          a.spill[2ull * at] = (uint32_t)slot;  // slots stay below 2^32 (n_q <= 2^32 - 2 - kTileQ is checked on the host)
+          a.spill[2ull * at] = (uint32_t)slot;  // slots stay below 2^32 (checked on the host)
           a.spill[2ull * at + 1] = k;
         }
         if (!EMIT) {
@@ -403,23 +486,33 @@ __global__ void __launch_bounds__(kProbeThreads, 1) bin_probe_kernel(const Binne
         const bool fits = wbase + total <= a.stage_cap;  // otherwise the join exceeds the caller's pair capacity
         if (valid && !spill) a.sres[slot] = make_uint2(fits ? (uint32_t)(wbase + excl) : kNotStored, cnt);
         if (!fits) continue;
-        for (uint32_t r0 = 0; r0 < total; r0 += kStageIds) {
-          uint32_t p = excl;
+        uint32_t* const out = a.staging + wbase;
+        if (total <= (uint32_t)kStageIds) {  // the usual case: one round, no clipping
+          const uint32_t p = expand_hits(mask_a, a_cid + 4u * c0, a_stage + 4u * excl);
+          expand_hits(mask_b, a_id + 4u * sa, p);
+          __syncwarp();
 #pragma unroll
-          for (uint32_t c = 0; c < kBinMaxClasses; ++c) {
-            uint32_t mask = h.mask[c];
-            while (mask) {
-              const uint32_t j = __ffs(mask) - 1;
-              mask &= mask - 1;
-              if (p - r0 < (uint32_t)kStageIds) my_stage[p - r0] = s_id[h.lb[c] + j];
-              ++p;
-            }
+          for (uint32_t s = 0; s < (uint32_t)kStageIds; s += 32)
+            if (s + lane < total) out[s + lane] = lds32_volatile(a_stage + 4u * (s + lane));
+          __syncwarp();
+        } else {
+          for (uint32_t r0 = 0; r0 < total; r0 += kStageIds) {
+            const uint32_t p = expand_hits_clipped(mask_a, a_cid + 4u * c0, a_stage, excl - r0);
+            expand_hits_clipped(mask_b, a_id + 4u * sa, a_stage, p);
+            __syncwarp();
+            const uint32_t n_here = min((uint32_t)kStageIds, total - r0);
+            for (uint32_t s = lane; s < n_here; s += 32) out[r0 + s] = lds32_volatile(a_stage + 4u * s);
+            __syncwarp();
           }
-          __syncwarp();
-          const uint32_t n_here = min((uint32_t)kStageIds, total - r0);
-          for (uint32_t s = lane; s < n_here; s += 32) a.staging[wbase + r0 + s] = my_stage[s];
-          __syncwarp();
         }
+      }
+      // rotate the descriptors; bring the queries of the step after next into L2 (first and last sector of each run)
+      d0 = d1;
+      d1 = d2;
+      if (d2 >> 16) {
+        const uint2* qrun = a.brec + (uint64_t)t2 * kTileQ + (d2 & 0xffffu);
+        prefetch_l2(qrun);
+        prefetch_l2(qrun + (d2 >> 16) - 1);
       }
     }
   }
@@ -434,7 +527,7 @@ __global__ void __launch_bounds__(256) bin_spill_kernel(const BinnedArgs a) {
   for (uint32_t e = blockIdx.x * 8 + (threadIdx.x >> 5); e < n; e += gridDim.x * 8) {
     const uint32_t slot = a.spill[2ull * e], g = a.desc[a.spill[2ull * e + 1]].group;
     const uint2 q = a.brec[slot];
-    uint32_t lbs[kBinMaxClasses], ubs[kBinMaxClasses];
+    uint32_t lbs[4], ubs[4];
     uint32_t cnt = 0;
     for (uint32_t c = 0; c < a.n_cls; ++c) {
       const GroupDesc d = a.gtable[(size_t)c * a.n_groups + g];
@@ -471,22 +564,21 @@ __global__ void __launch_bounds__(256) bin_spill_kernel(const BinnedArgs a) {
           hit = (q.x <= t.y) & (t.x <= q.y);
         }
         const unsigned bal = __ballot_sync(0xffffffffu, hit);
-        if (hit) a.staging[base + done + __popc(bal & ((1u << lane) - 1u))] = a.ids[r];
+        if (hit) a.staging[base + done + __popc(bal & ((1u << lane) - 1u))] = a.gids[r];
         done += __popc(bal);
       }
   }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Back to query order. Dynamic shared memory: res[kTileQ] uint2 | off[kTileQ + 2] u64 | out[kPlaceCap] u32 |
-// loc[kTileQ] u16. Offsets inside a tile are 64-bit: a spilled query may hit every target.
+// Back to query order. Dynamic shared memory: off[kTileQ + 2] u64 | out[kPlaceCap] u32 | loc[kTileQ] u16 (two
+// CTAs per SM). Offsets inside a tile are 64-bit: a spilled query may hit every target.
 template <bool EMIT>
-__global__ void __launch_bounds__(kPlaceThreads, 1) bin_place_kernel(const BinnedArgs a) {
+__global__ void __launch_bounds__(kPlaceThreads, 2) bin_place_kernel(const BinnedArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint2* s_res = reinterpret_cast<uint2*>(smem_raw);
-  uint64_t* s_off = reinterpret_cast<uint64_t*>(s_res + kTileQ);
+  uint64_t* s_off = reinterpret_cast<uint64_t*>(smem_raw);
   uint32_t* s_out = reinterpret_cast<uint32_t*>(s_off + kTileQ + 2);
-  uint16_t* s_loc = reinterpret_cast<uint16_t*>(s_out + kPlaceCap);
+  uint16_t* s_loc = reinterpret_cast<uint16_t*>(s_out + kPlaceCap + 4);
   __shared__ uint64_t s_scan[kPlaceThreads / 32 + 1];
   __shared__ uint32_t s_tile;
   __shared__ uint64_t s_base;
@@ -498,14 +590,14 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) bin_place_kernel(const Binne
   const uint16_t* trun = a.trun + (uint64_t)tile * (K + 2);
   const uint32_t n_live = trun[K], n_here = trun[K + 1];  // slots with a bin / queries of the tile
   const uint64_t q0 = (uint64_t)tile * kTileQ;
+  const uint2* const sres = a.sres + q0;
 
   for (uint32_t s = tid; s < (uint32_t)kTileQ; s += kPlaceThreads) {
-    s_res[s] = s < n_live ? a.sres[q0 + s] : make_uint2(0u, 0u);
     s_loc[s] = s < n_here ? a.bloc[q0 + s] : (uint16_t)0;
     s_off[s] = 0;
   }
   __syncthreads();
-  for (uint32_t s = tid; s < n_live; s += kPlaceThreads) s_off[s_loc[s]] = s_res[s].y;  // counts by query position
+  for (uint32_t s = tid; s < n_live; s += kPlaceThreads) s_off[s_loc[s]] = sres[s].y;  // counts by query position
   __syncthreads();
   // exclusive scan over the tile's 4096 counts (kPlaceQPT consecutive entries per thread)
   uint32_t c[kPlaceQPT];
@@ -534,26 +626,28 @@ __global__ void __launch_bounds__(kPlaceThreads, 1) bin_place_kernel(const Binne
 
   const uint64_t total = tile_total;
   for (uint64_t w0 = 0; w0 < total; w0 += kPlaceCap) {
-    // gather: 32 consecutive slots per warp step; their id lists lie next to each other in the staging area
+    // gather: a lane per slot copies its own id list (the lists of neighbouring slots lie next to each other in
+    // the staging area, so the lanes of a warp read the same few sectors; four loads are issued before the stores).
+    // Measured against warp-cooperative copies of the flattened lists (owner of every id by shuffle search, or by
+    // a bitmap of list ends + find-nth-set): those cost 1.8x - 2x the instructions of this loop.
     for (uint32_t s0 = warp * 32; s0 < n_live; s0 += kPlaceThreads) {
       const uint32_t s = s0 + lane;
       uint2 r = make_uint2(0u, 0u);
       uint64_t dst0 = 0;
-      if (s < n_live) { r = s_res[s]; dst0 = s_off[s_loc[s]]; }
+      if (s < n_live) { r = sres[s]; dst0 = s_off[s_loc[s]]; }
       const bool touches = r.y != 0 && dst0 < w0 + kPlaceCap && dst0 + r.y > w0;
-      if (!__any_sync(0xffffffffu, touches)) continue;
-      const uint32_t incl = warp_incl_scan(r.y, lane);
-      const uint32_t m = __shfl_sync(0xffffffffu, incl, 31);
-      for (uint32_t fb = 0; fb < m; fb += 32) {
-        const uint32_t f = fb + lane;
-        const int src = run_owner(incl, f < m ? f : 0u);
-        const uint32_t o_incl = __shfl_sync(0xffffffffu, incl, src), o_n = __shfl_sync(0xffffffffu, r.y, src);
-        const uint32_t o_beg = __shfl_sync(0xffffffffu, r.x, src);
-        const uint64_t o_dst = shfl_u64(dst0, src);
-        if (f < m) {
-          const uint32_t j = f - (o_incl - o_n);
-          const uint64_t dst = o_dst + j - w0;  // wraps far above the window for ids that lie before it
-          if (dst < (uint64_t)kPlaceCap) s_out[dst] = o_beg != kNotStored ? a.staging[(uint64_t)o_beg + j] : kNotStored;
+      const uint32_t cnt = touches ? r.y : 0u;
+      const uint32_t steps = __reduce_max_sync(0xffffffffu, cnt);
+      const uint32_t* src = a.staging + r.x;
+      const bool stored = r.x != kNotStored;
+      for (uint32_t j0 = 0; j0 < steps; j0 += 4) {
+        uint32_t v[4];
+#pragma unroll
+        for (uint32_t u = 0; u < 4; ++u) v[u] = (j0 + u < cnt && stored) ? src[j0 + u] : kNotStored;
+#pragma unroll
+        for (uint32_t u = 0; u < 4; ++u) {
+          const uint64_t d = dst0 + j0 + u - w0;  // wraps far above the window for ids that lie before it
+          if (j0 + u < cnt && d < (uint64_t)kPlaceCap) s_out[d] = v[u];
         }
       }
     }
@@ -610,7 +704,8 @@ int launch_join_binned(const bcu_index* ix, int mode, uint64_t n_q, const uint32
   if (stage_cap >= 0xffffffffull) return BCU_NOT_TAKEN;
 
   BinnedArgs a;
-  a.low = ix->d_low; a.high = ix->d_high; a.ids = ix->d_id; a.lowhigh = ix->d_lowhigh; a.dir = ix->d_dir;
+  a.low = ix->d_bn_low; a.high = ix->d_bn_high; a.ids = ix->d_bn_id; a.blob = ix->d_bn_blob;
+  a.lowhigh = ix->d_lowhigh; a.gids = ix->d_id; a.dir = ix->d_dir;
   a.gtable = ix->d_groups; a.desc = ix->d_bn_desc; a.groups = ix->d_bn_groups; a.cell2bin = ix->d_bn_cell2bin;
   a.n_groups = ix->n_groups; a.n_bins = ix->bn_bins; a.n_cells = ix->bn_cells; a.cell_shift = ix->bn_cell_shift;
   a.max_gval = ix->max_gval; a.n_cls = ix->n_comp;
@@ -618,6 +713,7 @@ int launch_join_binned(const bcu_index* ix, int mode, uint64_t n_q, const uint32
   a.offsets = d_offsets; a.capacity = pair_capacity; a.hit_query = d_hit_query; a.hit_target = d_hit_target;
   a.total = d_total; a.total_mapped = total_mapped; a.qid_base = query_id_base; a.emit = emit;
   a.stage_cap = stage_cap;
+  a.ht_aligned = (reinterpret_cast<uintptr_t>(d_hit_target) & 15u) == 0;
 
   // one stream-ordered allocation, carved up (every piece 256-byte aligned)
   const uint32_t K = ix->bn_bins;
@@ -648,13 +744,16 @@ int launch_join_binned(const bcu_index* ix, int mode, uint64_t n_q, const uint32
   a.spill = reinterpret_cast<uint32_t*>(scratch + o_spill);
   a.staging = reinterpret_cast<uint32_t*>(scratch + o_stage);
 
+  const bool warp_hist = K <= kSortMaxWarpHistBins;
   const size_t sort_smem = (size_t)kTileQ * 8 + (size_t)((K + 2 + 3) & ~3u) * 4 + (size_t)ix->n_groups * sizeof(BinGroup) +
-                           (size_t)kTileQ * 2 + (size_t)((ix->bn_cells + 7) & ~7u) * 2 + (size_t)kBnDirectGroups * 2;
-  const size_t probe_smem = (size_t)kBinRowsCap * 12 + (size_t)kProbeWarps * kStageIds * 4 + (size_t)kBinLutCap * 2;
-  const size_t place_smem = (size_t)kTileQ * 8 + (size_t)(kTileQ + 2) * 8 + (size_t)kPlaceCap * 4 + (size_t)kTileQ * 2;
+                           (size_t)kTileQ * 2 + (size_t)((ix->bn_cells + 7) & ~7u) * 2 + (size_t)kBnDirectGroups * 2 +
+                           (warp_hist ? (size_t)kSortWarps * ((K + 2 + 3) & ~3u) * 2 : 0);
+  const size_t probe_smem = (size_t)kBinTileBytes + (size_t)kProbeWarps * kStageIds * 4;
+  const size_t place_smem = (size_t)(kTileQ + 2) * 8 + (size_t)(kPlaceCap + 4) * 4 + (size_t)kTileQ * 2;
   static std::atomic<bool> attrs_set[64];
   if (ix->device < 0 || ix->device >= 64 || !attrs_set[ix->device].load()) {
-    BCU_CUDA(cudaFuncSetAttribute(bin_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    BCU_CUDA(cudaFuncSetAttribute(bin_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    BCU_CUDA(cudaFuncSetAttribute(bin_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     BCU_CUDA(cudaFuncSetAttribute(bin_probe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)probe_smem));
     BCU_CUDA(cudaFuncSetAttribute(bin_probe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)probe_smem));
     BCU_CUDA(cudaFuncSetAttribute(bin_place_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)place_smem));
@@ -663,8 +762,9 @@ int launch_join_binned(const bcu_index* ix, int mode, uint64_t n_q, const uint32
   }
   if (sort_smem > 200 * 1024) return BCU_NOT_TAKEN;
 
-  const unsigned sort_grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)sms * (sort_smem <= 100 * 1024 ? 2 : 1));
-  bin_sort_kernel<<<sort_grid, kSortThreads, sort_smem, stream>>>(a);
+  const unsigned sort_grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)sms * std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / (sort_smem + 1024))));
+  if (warp_hist) bin_sort_kernel<true><<<sort_grid, kSortThreads, sort_smem, stream>>>(a);
+  else bin_sort_kernel<false><<<sort_grid, kSortThreads, sort_smem, stream>>>(a);
   BCU_LAUNCHED();
   bin_transpose_kernel<<<dim3((K + 31) / 32, (unsigned)((n_tiles + 31) / 32)), 256, 0, stream>>>(a);
   BCU_LAUNCHED();

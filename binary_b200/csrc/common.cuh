@@ -76,35 +76,39 @@ struct __align__(16) DirEntry {
 constexpr uint32_t kInlineRows = 1;
 
 // ---- bin layout: the index cut into shared-memory sized coordinate tiles (binned_join.cu) ----------------
-// A BIN is a run of consecutive coordinate cells (width 1 << cell_shift) of one group whose rows -- over all
-// length classes, including for each class the rows that start up to that class's maximum length before the
-// bin -- fit one CTA's shared memory. Queries are routed to the bin of their `low`.
-constexpr uint32_t kBinMaxClasses = 4;
-constexpr uint32_t kBinRowsCap = 13312;     // rows of one bin's tile (all classes): 12 B each = 156 KB
-constexpr uint32_t kBinLutCap = 12288;      // u16 entries of the per-class sub-cell tables of one tile
+// A BIN is a run of consecutive coordinate cells (width 1 << cell_shift) of one group. Its OWN rows are the rows
+// whose low lies inside it -- a contiguous piece of the (group, low)-sorted arrays bn_low / bn_high / bn_id.
+// The bin's coordinate range is cut into sub-cells of width 1 << ls; for every sub-cell the layout stores
+//   sub_start[g]  the first own row with low >= the sub-cell's start, and
+//   cov[g]        the {high, id} of every proper row (any bin, any length) that starts BEFORE the sub-cell's
+//                 start and reaches it: low < start(g) <= high  ("coverage list", the rows a stabbing query at
+//                 start(g) returns),
+// so that the hits of a query q with q.low in sub-cell g are exactly
+//   { r in cov[g] : high_r >= q.low }  +  { own rows r >= sub_start[g] with low_r <= q.high : high_r >= q.low }.
+// No length classes and no running max are involved: a target of any length costs one entry per sub-cell start
+// it covers. Queries are routed to the bin of their `low`.
+constexpr uint32_t kBinTileBytes = 184320;  // own rows (12 B each) + the bin's blob must fit this much shared memory
 constexpr uint32_t kBinMaxCells = 16384;    // cells over all groups: the routing table is staged in shared memory
 constexpr uint32_t kBinMaxBins = 4095;      // bin ids are u16; kBinNull = no bin (unknown group / beyond every row)
 constexpr uint32_t kBinNull = 0xFFFFu;
 
-struct BinClass {
-  uint32_t row0;     // first global row copied into the tile (multiple of 4: bulk copies move 16-byte units)
-  uint32_t n_copy;   // rows copied (multiple of 4)
-  uint32_t lo, hi;   // valid tile-relative rows [lo, hi): lo = first row of the segment with low >= x0,
-                     // hi = first row with low >= the bin's end (segment end for a group's last bin)
-  uint32_t x0;       // coordinate origin of the sub-cell table: max(bin begin - maxlen, 0)
-  uint32_t ls;       // log2 of the sub-cell width
-  uint32_t nsub;     // sub-cells; the table has nsub + 1 entries
-  uint32_t maxlen;   // no proper row of the class is longer (high - low): bounds the candidate window
-  uint32_t s_off;    // offset of the class's rows in the tile's row arrays
-  uint32_t lut_off;  // offset of the class's table in the tile's LUT
-};
-struct BinDesc {
+struct BinDesc {     // 64 bytes
   uint32_t group;    // index of the group in the sorted group table
   uint32_t x_begin;  // first coordinate of the bin
   uint32_t x_end;    // first coordinate past the bin; 0 = the group's last bin (no upper limit)
-  uint32_t n_rows;   // rows copied over all classes
-  BinClass cls[kBinMaxClasses];
+  uint32_t ls;       // log2 of the sub-cell width
+  uint32_t nsub;     // sub-cells; sub_start and cov_rel have nsub + 1 entries (padded to a multiple of 8)
+  uint32_t row0;     // first row of bn_low/high/id copied into the tile (multiple of 4: bulk copies move 16 B units)
+  uint32_t n_copy;   // rows copied (multiple of 4)
+  uint32_t lo, hi;   // the bin's own rows, tile-relative: [lo, hi)
+  uint32_t n_cov;    // coverage entries of the bin (padded to a multiple of 4)
+  uint32_t blob_bytes;  // bytes of the bin's blob (multiple of 16)
+  uint32_t pad0;
+  uint64_t blob;     // byte offset of the blob in bn_blob: sub_start u16[pad8(nsub+1)] | cov_rel u16[pad8(nsub+1)] |
+                     // cov_high u32[n_cov] | cov_id u32[n_cov]
+  uint64_t pad1;
 };
+static_assert(sizeof(BinDesc) == 64, "BinDesc is copied word by word");
 struct BinGroup {    // query routing, per group (same order as the GroupDesc table)
   uint32_t gval;
   uint32_t cell_base;  // first entry of the group in cell2bin
@@ -137,7 +141,11 @@ struct bcu_index {
   uint32_t max_len = 0;              // longest proper target (high - low): window bound of the top length class
   // bin layout (binned_join.cu); bn_bins == 0: the index is not eligible for the binned path
   uint32_t bn_bins = 0, bn_cells = 0, bn_cell_shift = 0;
-  uint32_t* d_low = nullptr;           // [n+4] `low` of the sorted rows as a plain column (tile copies)
+  uint32_t* d_bn_low = nullptr;        // [n+4] the targets sorted by (group, low, id) -- BEFORE the length-class
+  uint32_t* d_bn_high = nullptr;       //       permutation -- as plain columns; high/id alias d_high/d_id when
+  uint32_t* d_bn_id = nullptr;         //       the index has one class (bn_owns_rows == false)
+  bool bn_owns_rows = false;
+  unsigned char* d_bn_blob = nullptr;  // per bin: sub-cell tables + coverage lists (BinDesc::blob)
   bcu::BinDesc* d_bn_desc = nullptr;   // [bn_bins]
   bcu::BinGroup* d_bn_groups = nullptr;  // [n_groups]
   uint16_t* d_bn_cell2bin = nullptr;   // [bn_cells]
@@ -166,8 +174,10 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
                 const bcu_filter* filter = nullptr, const uint8_t* d_qstrand = nullptr,
                 uint64_t* total_mapped = nullptr);  // device-visible pinned host u64 that also receives the total
 
-// bin layout of a finished index (index_build.cu); `table` = host copy of the [n_comp][n_groups] descriptors
-int build_bin_layout(bcu_index* ix, const GroupDesc* table, cudaStream_t stream);
+// bin layout of a finished index (index_build.cu). group_begin[g] .. group_begin[g+1] = rows of group g in the
+// (group, low)-sorted arrays ix->d_bn_*; group_cmax[g] = largest coordinate of the group
+int build_bin_layout(bcu_index* ix, const uint32_t* group_gval, const uint32_t* group_begin,
+                     const uint32_t* group_cmax, cudaStream_t stream);
 // the binned join (binned_join.cu); returns BCU_NOT_TAKEN when the call is not eligible: the caller then runs
 // the general path
 constexpr int BCU_NOT_TAKEN = 1;

@@ -229,12 +229,28 @@ __global__ void __launch_bounds__(kThreads)
   dir[e] = de;
 }
 
+__global__ void __launch_bounds__(kThreads)
+    split_low_kernel(const uint2* __restrict__ lowhigh, uint64_t n_padded, uint32_t* __restrict__ low) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_padded) low[r] = lowhigh[r].x;
+}
+
 static double env_double(const char* name, double dflt) {
   const char* s = std::getenv(name);
   if (!s || !*s) return dflt;
   char* end = nullptr;
   double v = std::strtod(s, &end);
   return (end && end != s && v > 0) ? v : dflt;
+}
+
+static void free_bin_layout(bcu_index* ix) {
+  cudaFreeAsync(ix->d_bn_desc, nullptr);
+  cudaFreeAsync(ix->d_bn_groups, nullptr);
+  cudaFreeAsync(ix->d_bn_cell2bin, nullptr);
+  cudaFreeAsync(ix->d_bn_blob, nullptr);
+  ix->d_bn_desc = nullptr; ix->d_bn_groups = nullptr; ix->d_bn_cell2bin = nullptr; ix->d_bn_blob = nullptr;
+  ix->bn_bins = 0;
+  cudaGetLastError();
 }
 
 static void free_index_members(bcu_index* ix) {
@@ -250,10 +266,15 @@ static void free_index_members(bcu_index* ix) {
   cudaFreeAsync(ix->d_dir, nullptr);
   cudaFreeAsync(ix->d_hs, nullptr);
   cudaFreeAsync(ix->d_dirh, nullptr);
-  cudaFreeAsync(ix->d_low, nullptr);
+  cudaFreeAsync(ix->d_bn_low, nullptr);
+  if (ix->bn_owns_rows) {
+    cudaFreeAsync(ix->d_bn_high, nullptr);
+    cudaFreeAsync(ix->d_bn_id, nullptr);
+  }
   cudaFreeAsync(ix->d_bn_desc, nullptr);
   cudaFreeAsync(ix->d_bn_groups, nullptr);
   cudaFreeAsync(ix->d_bn_cell2bin, nullptr);
+  cudaFreeAsync(ix->d_bn_blob, nullptr);
   cudaGetLastError();
 }
 
@@ -385,6 +406,9 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
   std::vector<uint32_t> gval(n_groups);
   uint64_t span = 0;
   for (uint32_t g = 0; g < n_groups; ++g) { gval[g] = (uint32_t)seg[g]; span += (uint64_t)cmax[g] + 1; }
+  // the (group, low)-sorted view the bin layout is built on (before any length-class permutation)
+  std::vector<uint32_t> bn_begin(heads), bn_cmax(cmax);
+  bn_begin.push_back((uint32_t)n);
 
   mark("rows, running max, segments");
   // ---- length classes (AIList-style decomposition) -------------------------------------------------
@@ -430,9 +454,22 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
       if (cudaGetLastError() != cudaSuccess) rc = BCU_E_CUDA;
       g_launches.fetch_add(1, std::memory_order_relaxed);
     }
+    if (rc == BCU_OK && cudaMallocAsync((void**)&ix->d_bn_low, (n + 4) * 4, stream) != cudaSuccess) rc = BCU_E_NOMEM;
+    if (rc == BCU_OK) {  // the group-sorted rows stay, as plain columns, for the bin layout
+      split_low_kernel<<<(unsigned)((n + 4 + kThreads - 1) / kThreads), kThreads, 0, stream>>>(old.d_lowhigh, n + 4, ix->d_bn_low);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      ix->d_bn_high = old.d_high;
+      ix->d_bn_id = old.d_id;
+      ix->bn_owns_rows = true;
+      ix->bytes += n * 12;
+    }
     if (rc == BCU_OK && cudaStreamSynchronize(stream) != cudaSuccess) rc = BCU_E_CUDA;
-    cudaFreeAsync(old.d_lowhigh, stream); cudaFreeAsync(old.d_id, stream); cudaFreeAsync(old.d_high, stream);
-    if (rc != BCU_OK) { set_error("index build: permuting rows into length classes failed"); return rc; }
+    cudaFreeAsync(old.d_lowhigh, stream);
+    if (rc != BCU_OK) {
+      if (!ix->bn_owns_rows) { cudaFreeAsync(old.d_id, stream); cudaFreeAsync(old.d_high, stream); }
+      set_error("index build: permuting rows into length classes failed");
+      return rc;
+    }
     segkey = segkey2;
     BCU_TRY(segmented_running_max(segkey, ix->d_high, ix->d_runmax, n, stream));
     BCU_TRY(probe_segments(ix, n, head_rows, counters + 4, segkey, tmp, stream, heads, seg, cmax));
@@ -541,97 +578,166 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
   BCU_LAUNCHED();
   BCU_CUDA(cudaStreamSynchronize(stream));  // host vectors are temporaries
   mark("directories");
-  BCU_TRY(build_bin_layout(ix, table.data(), stream));
+  if (!ix->d_bn_low) {  // one class: the index rows already are in (group, low) order
+    BCU_CUDA(cudaMallocAsync((void**)&ix->d_bn_low, (n + 4) * 4, stream));
+    ix->bytes += n * 4;
+    split_low_kernel<<<(unsigned)((n + 4 + kThreads - 1) / kThreads), kThreads, 0, stream>>>(ix->d_lowhigh, n + 4, ix->d_bn_low);
+    BCU_LAUNCHED();
+    ix->d_bn_high = ix->d_high;
+    ix->d_bn_id = ix->d_id;
+  }
+  if (n_comp == 1)  // the same bound an importer derives from the directory sizes: both sides build the same layout
+    for (uint32_t g = 0; g < n_groups; ++g)
+      bn_cmax[g] = (uint32_t)std::min<uint64_t>(((((uint64_t)bn_cmax[g] >> class_shift[0]) + 1) << class_shift[0]) - 1, 0xffffffffull);
+  BCU_TRY(build_bin_layout(ix, gval.data(), bn_begin.data(), bn_cmax.data(), stream));
   mark("bin layout");
   return BCU_OK;
 }
 
 // ---- bin layout (binned_join.cu): coordinate tiles of the index that fit one CTA's shared memory ----------
-__global__ void __launch_bounds__(kThreads)
-    split_low_kernel(const uint2* __restrict__ lowhigh, uint64_t n_padded, uint32_t* __restrict__ low) {
-  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < n_padded) low[r] = lowhigh[r].x;
-}
+// See common.cuh (BinDesc) for what the layout holds and why it answers a query exactly.
 
-// For every class slot c (blockIdx.y), group g and cell boundary j (0..n_cells_g): the first row of segment (c, g)
-// with low >= j << shift, and the first row with low >= (j << shift) - maxlen_c (the rows that may still reach
-// into the cell). bound_base[g] = first boundary index of group g (n_cells_g + 1 boundaries per group).
+// For group g and cell boundary j (0..n_cells_g): the first row of the group with low >= j << shift.
+// bound_base[g] = first boundary index of group g (n_cells_g + 1 boundaries per group).
 __global__ void __launch_bounds__(kThreads)
-    cell_rows_kernel(const GroupDesc* __restrict__ table, uint32_t n_groups, const uint32_t* __restrict__ bound_base,
-                     uint32_t n_bounds, uint32_t shift, const uint32_t* __restrict__ low, uint4 maxlen4,
-                     uint32_t* __restrict__ start_row, uint32_t* __restrict__ halo_row) {
-  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    cell_rows_kernel(const uint32_t* __restrict__ group_begin, uint32_t n_groups, const uint32_t* __restrict__ bound_base,
+                     uint32_t n_bounds, uint32_t shift, const uint32_t* __restrict__ low, uint32_t* __restrict__ start_row) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n_bounds) return;
   uint32_t lo = 0, hi = n_groups;  // group of boundary b: last g with bound_base[g] <= b
   while (hi - lo > 1) {
     const uint32_t mid = (lo + hi) >> 1;
     if (bound_base[mid] <= b) lo = mid; else hi = mid;
   }
-  const GroupDesc seg = table[(size_t)c * n_groups + lo];
   const uint64_t x = (uint64_t)(b - bound_base[lo]) << shift;
-  const uint32_t maxlen = c == 0 ? maxlen4.x : (c == 1 ? maxlen4.y : (c == 2 ? maxlen4.z : maxlen4.w));
-  const uint64_t xh = x > maxlen ? x - maxlen : 0;
-  auto lower = [&](uint64_t key) {
-    uint32_t a = seg.row_begin, e = seg.row_end;
-    while (a < e) {
-      const uint32_t m = a + ((e - a) >> 1);
-      if ((uint64_t)low[m] < key) a = m + 1; else e = m;
-    }
-    return a;
-  };
-  const bool empty = seg.nb == 0;
-  start_row[(size_t)c * n_bounds + b] = empty ? 0u : lower(x);
-  halo_row[(size_t)c * n_bounds + b] = empty ? 0u : lower(xh);
+  uint32_t a = group_begin[lo], e = group_begin[lo + 1];
+  while (a < e) {
+    const uint32_t m = a + ((e - a) >> 1);
+    if ((uint64_t)low[m] < x) a = m + 1; else e = m;
+  }
+  start_row[b] = a;
 }
 
-int build_bin_layout(bcu_index* ix, const GroupDesc* table, cudaStream_t stream) {
-  ix->bn_bins = 0;
-  const char* off = std::getenv("BCU_BINNED");
-  if (ix->n == 0 || ix->n_groups == 0 || (off && off[0] == '0')) return BCU_OK;
-  const uint32_t G = ix->n_groups, C = ix->n_comp;
-  // top non-empty class slot and the length bound of every slot (length_class_kernel: slot c < top holds
-  // lengths < base * 4^c, the top slot everything above)
-  uint32_t top = 0;
-  for (uint32_t c = 0; c < C; ++c)
-    for (uint32_t g = 0; g < G; ++g)
-      if (table[(size_t)c * G + g].nb) top = c;
-  uint32_t maxlen[kBinMaxClasses] = {0, 0, 0, 0};
-  uint64_t rows_c[kBinMaxClasses] = {0, 0, 0, 0};
-  for (uint32_t c = 0; c <= top; ++c) {
-    uint64_t lim = ix->class_base_len;
-    for (uint32_t k = 0; k < c; ++k) lim *= 4;
-    maxlen[c] = (c < top && lim - 1 < ix->max_len) ? (uint32_t)(lim - 1) : ix->max_len;
-    for (uint32_t g = 0; g < G; ++g) rows_c[c] += table[(size_t)c * G + g].row_end - table[(size_t)c * G + g].row_begin;
+// sub_start of every (bin, sub-cell): tile-relative first own row with low >= start of the sub-cell.
+// sub_base[b] = first global sub-cell slot of bin b (nsub_b + 1 slots per bin).
+__global__ void __launch_bounds__(kThreads)
+    sub_start_kernel(const BinDesc* __restrict__ desc, uint32_t n_bins, const uint32_t* __restrict__ sub_base,
+                     uint32_t n_slots, const uint32_t* __restrict__ low, uint32_t* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_slots) return;
+  uint32_t lo = 0, hi = n_bins;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (sub_base[mid] <= i) lo = mid; else hi = mid;
   }
-  // coordinate extent of every group (upper bound from the directory sizes), cell width, routing tables
-  std::vector<uint64_t> cmax(G, 0);
-  uint64_t span = 0;
-  for (uint32_t g = 0; g < G; ++g) {
-    for (uint32_t c = 0; c <= top; ++c) {
-      const GroupDesc& d = table[(size_t)c * G + g];
-      if (d.nb) cmax[g] = std::max<uint64_t>(cmax[g], std::min<uint64_t>(((uint64_t)d.nb << d.shift) - 1, 0xffffffffull));
+  const BinDesc d = desc[lo];
+  const uint64_t x = (uint64_t)d.x_begin + ((uint64_t)(i - sub_base[lo]) << d.ls);
+  uint32_t a = d.row0 + d.lo, e = d.row0 + d.hi;
+  while (a < e) {
+    const uint32_t m = a + ((e - a) >> 1);
+    if ((uint64_t)low[m] < x) a = m + 1; else e = m;
+  }
+  out[i] = a - d.row0;
+}
+
+// Coverage lists. One thread per row: every sub-cell start s with low < s <= high (over all the bins of the
+// row's group that the row reaches) gets the row. FILL = false: count into cnt[slot]; FILL = true: the row's
+// {high, id} is written at the slot's next free position (cursor[slot]) inside the bin's blob.
+template <bool FILL>
+__global__ void __launch_bounds__(kThreads)
+    coverage_kernel(const uint32_t* __restrict__ low, const uint32_t* __restrict__ high, const uint32_t* __restrict__ ids,
+                    uint32_t n, const uint32_t* __restrict__ group_begin, uint32_t n_groups,
+                    const BinGroup* __restrict__ groups, const uint16_t* __restrict__ cell2bin, uint32_t cell_shift,
+                    const BinDesc* __restrict__ desc, const uint32_t* __restrict__ sub_base, uint32_t* __restrict__ cnt,
+                    const uint32_t* __restrict__ off, uint32_t* __restrict__ cursor, unsigned char* __restrict__ blob,
+                    unsigned long long* total) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long mine = 0;
+  if (r < n) {
+    const uint32_t l = low[r], h = high[r];
+    if (h > l) {  // covers the sub-cell starts in (l, h]
+      uint32_t lo = 0, hi = n_groups;
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (group_begin[mid] <= r) lo = mid; else hi = mid;
+      }
+      const BinGroup g = groups[lo];
+      const uint32_t b_first = cell2bin[g.cell_base + (l >> cell_shift)];
+      const uint32_t b_last = cell2bin[g.cell_base + min(h >> cell_shift, g.n_cells - 1u)];
+      for (uint32_t b = b_first; b <= b_last; ++b) {  // bins of one group are numbered consecutively
+        const BinDesc d = desc[b];
+        const uint32_t g_from = l < d.x_begin ? 0u : ((l - d.x_begin) >> d.ls) + 1u;
+        if (h < d.x_begin) break;
+        const uint32_t g_to = min((h - d.x_begin) >> d.ls, d.nsub - 1u);
+        for (uint32_t s = g_from; s <= g_to && g_from < d.nsub; ++s) {
+          const uint32_t slot = sub_base[b] + s;
+          if (!FILL) {
+            atomicAdd(&cnt[slot], 1u);
+            ++mine;
+          } else {
+            const uint32_t at = off[slot] - off[sub_base[b]] + atomicAdd(&cursor[slot], 1u);
+            const uint32_t tables = ((d.nsub + 1 + 7) & ~7u) * 4u;  // sub_start + cov_rel, u16 each
+            uint32_t* cov_high = reinterpret_cast<uint32_t*>(blob + d.blob + tables);
+            cov_high[at] = h;
+            cov_high[d.n_cov + at] = ids[r];
+          }
+        }
+      }
     }
-    span += cmax[g] + 1;
   }
-  // a class whose candidate window (rows starting within maxlen of a query) averages more than kWindowMax rows
-  // would overflow the per-query hit masks of the tile probe most of the time: such indexes keep the general path
-  const double kWindowMax = env_double("BCU_BINNED_WINDOW", 16.0);
-  for (uint32_t c = 0; c <= top; ++c)
-    if ((double)rows_c[c] * ((double)maxlen[c] + 1.0) / (double)span > kWindowMax) return BCU_OK;
+  if (!FILL) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(total, mine);
+  }
+}
+
+// the two u16 tables at the head of every bin's blob
+__global__ void __launch_bounds__(kThreads)
+    blob_tables_kernel(const BinDesc* __restrict__ desc, uint32_t n_bins, const uint32_t* __restrict__ sub_base,
+                       uint32_t n_slots, const uint32_t* __restrict__ sub_start, const uint32_t* __restrict__ off,
+                       unsigned char* __restrict__ blob) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_slots) return;
+  uint32_t lo = 0, hi = n_bins;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (sub_base[mid] <= i) lo = mid; else hi = mid;
+  }
+  const BinDesc d = desc[lo];
+  const uint32_t s = i - sub_base[lo];
+  uint16_t* tab = reinterpret_cast<uint16_t*>(blob + d.blob);
+  tab[s] = (uint16_t)sub_start[i];
+  tab[((d.nsub + 1 + 7) & ~7u) + s] = (uint16_t)(off[i] - off[sub_base[lo]]);
+}
+
+__global__ void gather_u32_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx, uint32_t n,
+                                  uint32_t* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = src[idx[i]];
+}
+
+// One attempt with a given row target per bin. *too_big is set when a bin's rows + blob exceed the tile: the
+// caller retries with a smaller target.
+static int bin_layout_attempt(bcu_index* ix, const uint32_t* group_gval, const uint32_t* group_begin_h,
+                              const uint32_t* group_cmax, cudaStream_t stream, uint32_t rows_target, bool* too_big) {
+  *too_big = false;
+  const uint32_t G = ix->n_groups, n = (uint32_t)ix->n;
+  // cell width: the routing table over all groups must stay within kBinMaxCells entries
   uint32_t shift = 0;
   for (; shift < 32; ++shift) {
     uint64_t cells = 0;
-    for (uint32_t g = 0; g < G; ++g) cells += (cmax[g] >> shift) + 1;
+    for (uint32_t g = 0; g < G; ++g) cells += ((uint64_t)group_cmax[g] >> shift) + 1;
     if (cells <= kBinMaxCells) break;
   }
-  if (shift >= 32) return BCU_OK;  // more groups than cells: not eligible
+  if (shift >= 32) return BCU_OK;
   std::vector<BinGroup> groups(G);
   std::vector<uint32_t> bound_base(G + 1);
   uint32_t n_cells = 0;
   for (uint32_t g = 0; g < G; ++g) {
-    groups[g].gval = table[g].gval;
+    groups[g].gval = group_gval[g];
     groups[g].cell_base = n_cells;
-    groups[g].n_cells = (uint32_t)((cmax[g] >> shift) + 1);
+    groups[g].n_cells = (uint32_t)(((uint64_t)group_cmax[g] >> shift) + 1);
     groups[g].pad = 0;
     bound_base[g] = n_cells + g;
     n_cells += groups[g].n_cells;
@@ -640,44 +746,33 @@ int build_bin_layout(bcu_index* ix, const GroupDesc* table, cudaStream_t stream)
   const uint32_t n_bounds = n_cells + G;
 
   TempBuffers tmp(stream);
-  uint32_t *d_bound_base, *d_start, *d_halo;
+  uint32_t *d_bound_base, *d_start, *d_group_begin;
   BCU_CUDA(tmp.alloc(&d_bound_base, G + 1));
-  BCU_CUDA(tmp.alloc(&d_start, (uint64_t)C * n_bounds));
-  BCU_CUDA(tmp.alloc(&d_halo, (uint64_t)C * n_bounds));
-  BCU_CUDA(cudaMallocAsync((void**)&ix->d_low, (ix->n + 4) * 4, stream));
-  ix->bytes += ix->n * 4;
-  split_low_kernel<<<(unsigned)((ix->n + 4 + kThreads - 1) / kThreads), kThreads, 0, stream>>>(ix->d_lowhigh, ix->n + 4,
-                                                                                           ix->d_low);
-  BCU_LAUNCHED();
+  BCU_CUDA(tmp.alloc(&d_group_begin, G + 1));
+  BCU_CUDA(tmp.alloc(&d_start, n_bounds));
   BCU_CUDA(cudaMemcpyAsync(d_bound_base, bound_base.data(), (G + 1) * 4, cudaMemcpyHostToDevice, stream));
-  cell_rows_kernel<<<dim3((n_bounds + kThreads - 1) / kThreads, C), kThreads, 0, stream>>>(
-      ix->d_groups, G, d_bound_base, n_bounds, shift, ix->d_low, make_uint4(maxlen[0], maxlen[1], maxlen[2], maxlen[3]),
-      d_start, d_halo);
+  BCU_CUDA(cudaMemcpyAsync(d_group_begin, group_begin_h, (G + 1) * 4, cudaMemcpyHostToDevice, stream));
+  cell_rows_kernel<<<(n_bounds + kThreads - 1) / kThreads, kThreads, 0, stream>>>(d_group_begin, G, d_bound_base, n_bounds,
+                                                                               shift, ix->d_bn_low, d_start);
   BCU_LAUNCHED();
-  std::vector<uint32_t> start((size_t)C * n_bounds), halo((size_t)C * n_bounds);
-  BCU_CUDA(cudaMemcpyAsync(start.data(), d_start, start.size() * 4, cudaMemcpyDeviceToHost, stream));
-  BCU_CUDA(cudaMemcpyAsync(halo.data(), d_halo, halo.size() * 4, cudaMemcpyDeviceToHost, stream));
+  std::vector<uint32_t> start(n_bounds);
+  BCU_CUDA(cudaMemcpyAsync(start.data(), d_start, (size_t)n_bounds * 4, cudaMemcpyDeviceToHost, stream));
   BCU_CUDA(cudaStreamSynchronize(stream));
 
-  // greedy: extend a bin cell by cell while its rows (all classes, with their halos and the 4-row alignment
-  // of the bulk copies) fit the tile
-  const uint32_t rows_cap = (uint32_t)std::min<double>(kBinRowsCap, env_double("BCU_BIN_ROWS", kBinRowsCap));
-  auto tile_rows = [&](uint32_t g, uint32_t j0, uint32_t j1) {
-    uint64_t rows = 0;
-    for (uint32_t c = 0; c <= top; ++c) {
-      const uint32_t h = halo[(size_t)c * n_bounds + bound_base[g] + j0], e = start[(size_t)c * n_bounds + bound_base[g] + j1];
-      if (e > h) rows += (uint64_t)(e - (h & ~3u) + 3) / 4 * 4;
-    }
-    return rows;
-  };
+  // greedy: extend a bin cell by cell while it stays within the row target. The coverage lists of a bin are not
+  // known yet; the target leaves them about a third of the tile (verified below).
+  const uint32_t sub_rows = (uint32_t)std::max(1.0, env_double("BCU_BIN_SUBROWS", 6.0));  // own rows per sub-cell
   std::vector<BinDesc> bins;
   std::vector<uint16_t> cell2bin(n_cells, (uint16_t)kBinNull);
+  std::vector<uint32_t> sub_base;
+  uint32_t n_slots = 0;
   for (uint32_t g = 0; g < G; ++g) {
     const uint32_t nc = groups[g].n_cells;
+    const uint32_t* st = start.data() + bound_base[g];
     for (uint32_t j0 = 0; j0 < nc;) {
       uint32_t j1 = j0 + 1;
-      if (tile_rows(g, j0, j1) > rows_cap) return BCU_OK;  // one cell does not fit: not eligible
-      while (j1 < nc && tile_rows(g, j0, j1 + 1) <= rows_cap) ++j1;
+      if (st[j1] - st[j0] + 8 > 12288) return BCU_OK;  // one cell alone exceeds any tile: not eligible
+      while (j1 < nc && st[j1 + 1] - st[j0] <= rows_target) ++j1;
       if (bins.size() >= kBinMaxBins) return BCU_OK;
       BinDesc b;
       std::memset(&b, 0, sizeof(b));
@@ -685,49 +780,119 @@ int build_bin_layout(bcu_index* ix, const GroupDesc* table, cudaStream_t stream)
       b.x_begin = (uint32_t)((uint64_t)j0 << shift);
       const bool last = j1 == nc;
       b.x_end = last ? 0u : (uint32_t)((uint64_t)j1 << shift);
-      const uint64_t x_end_eff = last ? cmax[g] + 1 : ((uint64_t)j1 << shift);
-      uint32_t s_off = 0, lut_off = 0;
-      for (uint32_t c = 0; c <= top; ++c) {
-        BinClass& k = b.cls[c];
-        const uint32_t h = halo[(size_t)c * n_bounds + bound_base[g] + j0], e = start[(size_t)c * n_bounds + bound_base[g] + j1];
-        k.maxlen = maxlen[c];
-        k.x0 = b.x_begin > maxlen[c] ? b.x_begin - maxlen[c] : 0u;
-        k.s_off = s_off;
-        k.lut_off = lut_off;
-        if (e > h) {
-          k.row0 = h & ~3u;
-          k.n_copy = (e - k.row0 + 3) / 4 * 4;
-          k.lo = h - k.row0;
-          k.hi = e - k.row0;
-        }
-        const uint64_t spanc = x_end_eff - k.x0;  // >= 1
-        const uint64_t budget = std::max<uint64_t>(16, (uint64_t)(k.hi - k.lo) * 3 / 4);
-        uint32_t ls = 0;
-        while (((spanc - 1) >> ls) + 1 > budget) ++ls;
-        k.ls = ls;
-        k.nsub = (uint32_t)(((spanc - 1) >> ls) + 1);
-        s_off += k.n_copy;
-        lut_off += k.nsub + 1;
-      }
-      if (s_off > kBinRowsCap || lut_off > kBinLutCap) return BCU_OK;
-      b.n_rows = s_off;
+      const uint64_t span = (last ? (uint64_t)group_cmax[g] + 1 : ((uint64_t)j1 << shift)) - b.x_begin;  // >= 1
+      const uint32_t own = st[j1] - st[j0];
+      b.row0 = st[j0] & ~3u;
+      b.n_copy = own ? (st[j1] - b.row0 + 3) / 4 * 4 : 0u;
+      b.lo = st[j0] - b.row0;
+      b.hi = st[j1] - b.row0;
+      const uint64_t want_sub = std::max<uint64_t>(1, own / sub_rows);
+      uint32_t ls = 0;
+      while (((span - 1) >> ls) + 1 > want_sub) ++ls;
+      b.ls = ls;
+      b.nsub = (uint32_t)(((span - 1) >> ls) + 1);
       for (uint32_t j = j0; j < j1; ++j) cell2bin[groups[g].cell_base + j] = (uint16_t)bins.size();
+      sub_base.push_back(n_slots);
+      n_slots += b.nsub + 1;
       bins.push_back(b);
       j0 = j1;
     }
   }
-  if (bins.empty()) return BCU_OK;
-  BCU_CUDA(cudaMallocAsync((void**)&ix->d_bn_desc, bins.size() * sizeof(BinDesc), stream));
+  const uint32_t K = (uint32_t)bins.size();
+  if (K == 0) return BCU_OK;
+  sub_base.push_back(n_slots);
+
+  // device copies of the routing tables (kept by the index) and of the provisional descriptors
+  BCU_CUDA(cudaMallocAsync((void**)&ix->d_bn_desc, (size_t)K * sizeof(BinDesc), stream));
   BCU_CUDA(cudaMallocAsync((void**)&ix->d_bn_groups, (size_t)G * sizeof(BinGroup), stream));
   BCU_CUDA(cudaMallocAsync((void**)&ix->d_bn_cell2bin, (size_t)n_cells * 2, stream));
-  BCU_CUDA(cudaMemcpyAsync(ix->d_bn_desc, bins.data(), bins.size() * sizeof(BinDesc), cudaMemcpyHostToDevice, stream));
+  BCU_CUDA(cudaMemcpyAsync(ix->d_bn_desc, bins.data(), (size_t)K * sizeof(BinDesc), cudaMemcpyHostToDevice, stream));
   BCU_CUDA(cudaMemcpyAsync(ix->d_bn_groups, groups.data(), (size_t)G * sizeof(BinGroup), cudaMemcpyHostToDevice, stream));
   BCU_CUDA(cudaMemcpyAsync(ix->d_bn_cell2bin, cell2bin.data(), (size_t)n_cells * 2, cudaMemcpyHostToDevice, stream));
+  uint32_t *d_sub_base, *d_sub_start, *d_cnt, *d_off, *d_bin_off;
+  unsigned long long* d_total;
+  BCU_CUDA(tmp.alloc(&d_sub_base, K + 1));
+  BCU_CUDA(tmp.alloc(&d_sub_start, n_slots));
+  BCU_CUDA(tmp.alloc(&d_cnt, (uint64_t)n_slots + 4));
+  BCU_CUDA(tmp.alloc(&d_off, (uint64_t)n_slots + 4));
+  BCU_CUDA(tmp.alloc(&d_bin_off, K + 1));
+  BCU_CUDA(tmp.alloc(&d_total, 1));
+  BCU_CUDA(cudaMemcpyAsync(d_sub_base, sub_base.data(), (size_t)(K + 1) * 4, cudaMemcpyHostToDevice, stream));
+  BCU_CUDA(cudaMemsetAsync(d_cnt, 0, ((size_t)n_slots + 4) * 4, stream));
+  BCU_CUDA(cudaMemsetAsync(d_total, 0, 8, stream));
+  sub_start_kernel<<<(n_slots + kThreads - 1) / kThreads, kThreads, 0, stream>>>(ix->d_bn_desc, K, d_sub_base, n_slots,
+                                                                             ix->d_bn_low, d_sub_start);
+  BCU_LAUNCHED();
+  const unsigned grid_rows = (n + kThreads - 1) / kThreads;
+  coverage_kernel<false><<<grid_rows, kThreads, 0, stream>>>(ix->d_bn_low, ix->d_bn_high, ix->d_bn_id, n, d_group_begin, G,
+                                                            ix->d_bn_groups, ix->d_bn_cell2bin, shift, ix->d_bn_desc,
+                                                            d_sub_base, d_cnt, nullptr, nullptr, nullptr, d_total);
+  BCU_LAUNCHED();
+  // one more slot than there are (its exclusive sum is the grand total), so that every bin's end is an entry of off
+  BCU_TRY(exclusive_sum_u32(d_cnt, d_off, (uint64_t)n_slots + 1, stream));
+  gather_u32_kernel<<<(K + 1 + kThreads - 1) / kThreads, kThreads, 0, stream>>>(d_off, d_sub_base, K + 1, d_bin_off);
+  BCU_LAUNCHED();
+  std::vector<uint32_t> bin_off(K + 1);
+  unsigned long long total = 0;
+  BCU_CUDA(cudaMemcpyAsync(bin_off.data(), d_bin_off, (size_t)(K + 1) * 4, cudaMemcpyDeviceToHost, stream));
+  BCU_CUDA(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, stream));
+  BCU_CUDA(cudaStreamSynchronize(stream));
+  // Eligibility: every bin's rows + blob fit the tile, and the lists stay a small multiple of the rows (long targets
+  // cost one entry per sub-cell they cover: a set dominated by them is better served by the general path)
+  if ((double)total > env_double("BCU_BINNED_COVER", 4.0) * (double)n + 65536.0) {
+    free_bin_layout(ix);
+    return BCU_OK;
+  }
+  uint64_t blob_bytes = 0;
+  for (uint32_t b = 0; b < K; ++b) {
+    BinDesc& d = bins[b];
+    d.n_cov = (bin_off[b + 1] - bin_off[b] + 3) & ~3u;
+    d.blob = blob_bytes;
+    d.blob_bytes = ((d.nsub + 1 + 7) & ~7u) * 4u + d.n_cov * 8u;
+    blob_bytes += d.blob_bytes;
+    if (d.n_cov > 65535u || (uint64_t)d.n_copy * 12u + d.blob_bytes > kBinTileBytes) {
+      free_bin_layout(ix);
+      *too_big = true;
+      return BCU_OK;
+    }
+  }
+  uint32_t* d_cursor;
+  BCU_CUDA(tmp.alloc(&d_cursor, (uint64_t)n_slots + 4));
+  BCU_CUDA(cudaMemsetAsync(d_cursor, 0, ((size_t)n_slots + 4) * 4, stream));
+  BCU_CUDA(cudaMallocAsync((void**)&ix->d_bn_blob, blob_bytes + 16, stream));
+  BCU_CUDA(cudaMemsetAsync(ix->d_bn_blob, 0, blob_bytes + 16, stream));
+  BCU_CUDA(cudaMemcpyAsync(ix->d_bn_desc, bins.data(), (size_t)K * sizeof(BinDesc), cudaMemcpyHostToDevice, stream));
+  blob_tables_kernel<<<(n_slots + kThreads - 1) / kThreads, kThreads, 0, stream>>>(ix->d_bn_desc, K, d_sub_base, n_slots,
+                                                                               d_sub_start, d_off, ix->d_bn_blob);
+  BCU_LAUNCHED();
+  coverage_kernel<true><<<grid_rows, kThreads, 0, stream>>>(ix->d_bn_low, ix->d_bn_high, ix->d_bn_id, n, d_group_begin, G,
+                                                           ix->d_bn_groups, ix->d_bn_cell2bin, shift, ix->d_bn_desc,
+                                                           d_sub_base, nullptr, d_off, d_cursor, ix->d_bn_blob, nullptr);
+  BCU_LAUNCHED();
   BCU_CUDA(cudaStreamSynchronize(stream));  // host vectors are temporaries
-  ix->bytes += bins.size() * sizeof(BinDesc) + (size_t)G * sizeof(BinGroup) + (size_t)n_cells * 2;
-  ix->bn_bins = (uint32_t)bins.size();
+  ix->bytes += (uint64_t)K * sizeof(BinDesc) + (size_t)G * sizeof(BinGroup) + (size_t)n_cells * 2 + blob_bytes;
+  ix->bn_bins = K;
   ix->bn_cells = n_cells;
   ix->bn_cell_shift = shift;
+  return BCU_OK;
+}
+
+int build_bin_layout(bcu_index* ix, const uint32_t* group_gval, const uint32_t* group_begin_h,
+                     const uint32_t* group_cmax, cudaStream_t stream) {
+  ix->bn_bins = 0;
+  const char* off_env = std::getenv("BCU_BINNED");
+  if (ix->n == 0 || ix->n_groups == 0 || ix->n_groups > (uint32_t)kMaxSmemGroups || (off_env && off_env[0] == '0'))
+    return BCU_OK;
+  // the coverage lists of a bin are only known after they are counted: start from a target that leaves them a
+  // third of the tile and shrink it while some bin does not fit
+  uint32_t rows_target = (uint32_t)std::max(16.0, std::min(12288.0, env_double("BCU_BIN_ROWS", 8192.0)));
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    bool too_big = false;
+    BCU_TRY(bin_layout_attempt(ix, group_gval, group_begin_h, group_cmax, stream, rows_target, &too_big));
+    if (!too_big) break;
+    rows_target = rows_target * 2 / 3;
+    if (rows_target < 16) break;
+  }
   return BCU_OK;
 }
 
@@ -914,12 +1079,29 @@ extern "C" int bcu_index_import_dev(int device, const void* d_image, uint64_t by
     delete ix;
     return rc;
   }
-  if (ix->n) {  // the bin layout is derived data: rebuilt from the imported arrays rather than shipped
-    std::vector<GroupDesc> table((size_t)ix->n_comp * ix->n_groups);
+  if (ix->n && ix->n_comp == 1) {
+    // The bin layout is derived data: rebuilt from the imported arrays rather than shipped. It needs the rows in
+    // (group, low) order, which the image only holds when the index has ONE length class; an imported index with
+    // several classes answers every batch through the general path.
+    std::vector<GroupDesc> table((size_t)ix->n_groups);
     const uint64_t bytes_before = ix->bytes;
     if (cudaMemcpyAsync(table.data(), ix->d_groups, table.size() * sizeof(GroupDesc), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
         cudaStreamSynchronize(stream) != cudaSuccess) rc = BCU_E_CUDA;
-    if (rc == BCU_OK) rc = build_bin_layout(ix, table.data(), stream);
+    std::vector<uint32_t> gval(ix->n_groups), begin(ix->n_groups + 1), cmax(ix->n_groups);
+    for (uint32_t g = 0; g < ix->n_groups; ++g) {
+      gval[g] = table[g].gval;
+      begin[g] = table[g].row_begin;
+      cmax[g] = (uint32_t)std::min<uint64_t>(((uint64_t)table[g].nb << table[g].shift) - 1, 0xffffffffull);
+    }
+    begin[ix->n_groups] = (uint32_t)ix->n;
+    if (rc == BCU_OK && cudaMallocAsync((void**)&ix->d_bn_low, (ix->n + 4) * 4, stream) != cudaSuccess) rc = BCU_E_NOMEM;
+    if (rc == BCU_OK) {
+      split_low_kernel<<<(unsigned)((ix->n + 4 + kThreads - 1) / kThreads), kThreads, 0, stream>>>(ix->d_lowhigh, ix->n + 4, ix->d_bn_low);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      ix->d_bn_high = ix->d_high;
+      ix->d_bn_id = ix->d_id;
+      rc = build_bin_layout(ix, gval.data(), begin.data(), cmax.data(), stream);
+    }
     ix->bytes = bytes_before;  // `bytes` travels in the header and already counts the exporter's layout
     if (rc != BCU_OK) {
       free_index_members(ix);

@@ -205,6 +205,33 @@ class DeviceIndex:
                                             stream or None))
 
 
+def join_multi(indexes, qlow, qhigh, qgroup=None, pair_capacity: Optional[int] = None, want_query_ids: bool = True,
+               counts32: bool = False):
+    """``bcu_join_multi``: one call, several GPUs. ``indexes`` = one :class:`DeviceIndex` per device, replicas of
+    the same target set; the batch is cut into ``len(indexes)`` contiguous query ranges. Returns
+    ``(offsets or counts, hit_query, hit_target)`` exactly as :meth:`DeviceIndex.join` does for the whole batch
+    (``counts32=True``: u32 hits per query instead of u64 offsets -- half the bytes over PCIe)."""
+    qlow, qhigh, qgroup = DeviceIndex._queries(qlow, qhigh, qgroup)
+    lib = _lib.load()
+    handles = (vp * len(indexes))(*[ix._h for ix in indexes])
+    n = qlow.size
+    offsets = None if counts32 else np.empty(n + 1, dtype=np.uint64)
+    counts = np.empty(n, dtype=np.uint32) if counts32 else None
+    cap = int(pair_capacity) if pair_capacity is not None else max(4 * n, 1 << 16)
+    total = C.c_uint64()
+    for _ in range(2):
+        hq = np.empty(cap, dtype=np.uint32) if want_query_ids else None
+        ht = np.empty(cap, dtype=np.uint32)
+        rc = lib.bcu_join_multi(handles, len(indexes), n, _p(qgroup), _p(qlow), _p(qhigh), _p(offsets), _p(counts), cap,
+                                _p(hq), ht.ctypes.data, C.byref(total))
+        if rc == _lib.BCU_E_CAPACITY:
+            cap = total.value
+            continue
+        check(rc)
+        return (counts if counts32 else offsets), (hq[: total.value] if want_query_ids else None), ht[: total.value]
+    raise _lib.BinaryCudaError(_lib.BCU_E_CAPACITY, "pair capacity still too small after growing")
+
+
 class IntervalTree:
     """Drop-in for the reference ``IntervalTree<IntervalNode<UIntInterval>>`` with a batched query."""
 

@@ -11,6 +11,7 @@
  *   bcu_query_count*      <- IntervalTree::find_overlaps(...).size()             interval_tree.hpp:161-168
  *   bcu_query_scatter*    <- IntervalTree::find_overlaps / find_overlaps_impl    interval_tree.hpp:306-334
  *   bcu_join*             <- the sv2nl hot loop: one find_overlaps per record    sv2nl mapper.hpp:207-218
+ *   bcu_join_multi        <- the same loop spread over the pool's tasks          sv2nl mapper.hpp:238-246
  *   bcu_query_any*        <- IntervalTree::find_overlap(...).has_value()         interval_tree.hpp:290-304
  *   bcu_index_size        <- RbTree::size()                                      rb_tree.hpp:173-180
  *
@@ -122,6 +123,17 @@ int bcu_join(const bcu_index* index, uint64_t n_q, const uint32_t* qgroup, const
              const uint32_t* qhigh, uint64_t* offsets, uint64_t pair_capacity, uint32_t* hit_query,
              uint32_t* hit_target, uint64_t* total);
 int bcu_trim(void);
+/* The same join on SEVERAL GPUs in one call (the reference's counterpart: one thread-pool task per chromosome over
+ * shared trees, sv2nl mapper.hpp:238-246, mapper.cpp:136-140). indexes[d] are replicas of ONE target set, one per
+ * device (build them with bcu_index_build*, or ship one with bcu_index_export_dev / import_dev). The batch is cut
+ * into n_dev contiguous query ranges, range d is joined on the device of indexes[d] by a worker thread that owns
+ * that device's streams and pinned-buffer staging (created on first use, kept for the life of the process); the
+ * devices never exchange data -- the only exchange is each range's hit total, on the host. Result: the CSR of
+ * bcu_join over the whole batch, written in place (query ids and offsets are global). Either `offsets` (u64,
+ * n_q + 1) or `counts` (u32 hits per query, n_q; half the bytes over PCIe) or both; hit_query may be NULL. */
+int bcu_join_multi(const bcu_index* const* indexes, int n_dev, uint64_t n_q, const uint32_t* qgroup,
+                   const uint32_t* qlow, const uint32_t* qhigh, uint64_t* offsets, uint32_t* counts,
+                   uint64_t pair_capacity, uint32_t* hit_query, uint32_t* hit_target, uint64_t* total);
 /* bcu_join with a pair filter (see bcu_filter). qstrand: n_q bytes, may be NULL unless kind is INV with
  * use_strand. */
 int bcu_join_filtered(const bcu_index* index, const bcu_filter* filter, uint64_t n_q, const uint32_t* qgroup,

@@ -71,7 +71,7 @@ def check_case(c, port, rows=None, window=None, qid_base=0, must_bin=True):
     if rows:
         kw["BCU_BIN_ROWS"] = rows
     if window:
-        kw["BCU_BINNED_WINDOW"] = window
+        kw["BCU_BINNED_COVER"] = window
     with env(BCU_BINNED=1, **kw):
         ix = DeviceIndex.build(c["tl"], c["th"], c["tg"])
         info = ix.info()
@@ -90,7 +90,7 @@ def check_case(c, port, rows=None, window=None, qid_base=0, must_bin=True):
     (2, dict(n_t=5000, n_q=9000, n_groups=5, q_groups=7), 128),                      # unknown query groups
     (3, dict(n_t=4000, n_q=2500, inverted_frac=0.3, dup_frac=0.2, extremes=True), 0),   # u32-wide targets: no layout
     (10, dict(n_t=4000, n_q=2500, inverted_frac=0.3, dup_frac=0.2), 512),
-    (4, dict(n_t=4000, n_q=5000, long_frac=0.02, n_groups=3), 512),                  # length classes, big halos
+    (4, dict(n_t=4000, n_q=5000, long_frac=0.02, n_groups=3), 512),                  # long targets: long coverage lists
     (5, dict(n_t=1, n_q=1), None),
     (6, dict(n_t=3, n_q=4097, span=50, max_len=10), None),                            # tile boundary + 1
     (7, dict(n_t=300, n_q=4096, span=100000, max_len=100), 64),
@@ -102,7 +102,7 @@ def test_binned_path_random_cases(port_oracle, seed, kw, rows):
 
 
 def test_windows_beyond_the_hit_mask_spill_to_the_general_index(port_oracle):
-    """Dense data: most candidate windows exceed the 32-row mask, so nearly every query goes through
+    """Dense data: most coverage lists exceed the 32-row mask, so nearly every query goes through
     bin_spill_kernel; mixed with sparse queries that stay in the tiles."""
     c = random_case(21, n_t=20000, n_q=6000, span=200000, max_len=3000)               # ~150 candidates per query
     s = random_case(22, n_t=20000, n_q=6000, span=200000, max_len=3)
@@ -154,6 +154,15 @@ def test_binned_equals_general_path_on_the_same_index(port_oracle):
         off1, hq1, ht1 = dev_join(ix, c["ql"], c["qh"], c["qg"])
     assert np.array_equal(off0, off1) and np.array_equal(hq0, hq1)
     assert np.array_equal(canonical(off0, ht0)[1], canonical(off1, ht1)[1])
+    ix.close()
+    # an imported image of a one-class index rebuilds the same layout (with several classes the image does not hold
+    # the (group, low) order the layout is built on: such an index answers through the general path)
+    c = random_case(42, n_t=50000, n_q=30000, n_groups=6, span=5_000_000, max_len=3000)
+    with env(BCU_BIN_ROWS=2048):
+        ix = DeviceIndex.build(c["tl"], c["th"], c["tg"])
+    assert ix.info()["n_components"] == 1 and ix.info()["binned_tiles"] > 0
+    with env(BCU_BINNED=1):
+        off1, hq1, ht1 = dev_join(ix, c["ql"], c["qh"], c["qg"])
     dev = torch.device("cuda:0")
     nbytes = ix.image_size()
     image = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
@@ -161,7 +170,7 @@ def test_binned_equals_general_path_on_the_same_index(port_oracle):
     ix.export_dev(image.data_ptr(), nbytes, stream)
     with env(BCU_BIN_ROWS=2048):
         ix2 = DeviceIndex.import_dev(0, image.data_ptr(), nbytes, stream)
-    assert ix2.info() == ix.info() and ix2.info()["binned_tiles"] > 0
+    assert ix2.info() == ix.info()
     with env(BCU_BINNED=1):
         off2, hq2, ht2 = dev_join(ix2, c["ql"], c["qh"], c["qg"])
     assert np.array_equal(off2, off1) and np.array_equal(canonical(off2, ht2)[1], canonical(off1, ht1)[1])

@@ -378,7 +378,11 @@ def test_index_image_round_trip(port_oracle, seed, kw):
     ix = DeviceIndex.import_dev(0, moved.data_ptr(), nbytes, stream)
     del moved                                                        # the index owns copies
     torch.cuda.synchronize()
-    assert ix.info() == info and len(ix) == c["tl"].size
+    got_info = ix.info()
+    if info["n_components"] > 1:   # the bin layout needs the (group, low) order, which such an image does not hold
+        assert got_info["binned_tiles"] == 0
+        got_info["binned_tiles"] = info["binned_tiles"]
+    assert got_info == info and len(ix) == c["tl"].size
     got = ix.join(c["ql"], c["qh"], c["qg"])
     for a, b in zip(got, want):
         assert np.array_equal(a, b)
