@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(kSortThreads, 2) bin_sort_kernel(const BinnedA
     for (int j = 0; j < kSortQPT; ++j)
       if (bin[j] <= K) {
         const uint32_t slot = s_hist[bin[j]] + rank[j] + (WARP_HIST ? (uint32_t)s_whist[warp * Kp + bin[j]] : 0u);
+        BCU_DEV_ASSERT(slot < (uint32_t)kTileQ);
         s_rec[slot] = make_uint2(ql[j], qh[j]);
         s_loc[slot] = (uint16_t)(j * kSortThreads + tid);
       }
@@ -439,16 +440,19 @@ __global__ void __launch_bounds__(kProbeThreads, 1) bin_probe_kernel(const Binne
         const uint32_t o_start = __shfl_sync(0xffffffffu, r_start, src);
         const uint64_t slot = (uint64_t)(t0 + src) * kTileQ + o_start + (f - (o_incl - o_n));
         uint2 q = make_uint2(x_begin, x_begin);
+        BCU_DEV_ASSERT(!valid || slot < (uint64_t)a.n_tiles * kTileQ);
         if (valid) q = a.brec[slot];
         const uint32_t ql = q.x, qh = q.y;
 
         // candidates: the coverage list of q.low's sub-cell + the own rows from that sub-cell's start up to q.high
         const uint32_t g = (ql - x_begin) >> ls;  // < nsub: the query was routed here by q.low
+        BCU_DEV_ASSERT(ql >= x_begin && g < nsub);
         const uint32_t c0 = lds16(a_rel + 2u * g), wa = lds16(a_rel + 2u * g + 2u) - c0;
         const uint32_t sa = lds16(a_sub + 2u * g);
         uint32_t ub = lds16(a_sub + 2u * min((max(qh, ql) - x_begin) >> ls, nsub - 1u) + 2u);
         while (ub > sa && lds32(a_low + 4u * ub - 4u) > qh) --ub;  // back over the own rows that start beyond q.high
         const uint32_t wb = ub > sa ? ub - sa : 0u;
+        BCU_DEV_ASSERT(c0 + wa <= n_cov && ub <= n_copy && sa <= n_copy && 12u * n_copy + s_desc.blob_bytes <= kBinTileBytes);
         // the general index answers: inverted queries, queries that reach past the bin, windows beyond the mask
         const bool spill = valid && (qh < ql || (x_end != 0 && qh >= x_end) || wa > kMaskRows || wb > kMaskRows);
         uint32_t mask_a = 0, mask_b = 0;
@@ -487,6 +491,7 @@ __global__ void __launch_bounds__(kProbeThreads, 1) bin_probe_kernel(const Binne
         if (valid && !spill) a.sres[slot] = make_uint2(fits ? (uint32_t)(wbase + excl) : kNotStored, cnt);
         if (!fits) continue;
         uint32_t* const out = a.staging + wbase;
+        BCU_DEV_ASSERT(wbase + total <= a.stage_cap && excl + cnt <= total);
         if (total <= (uint32_t)kStageIds) {  // the usual case: one round, no clipping
           const uint32_t p = expand_hits(mask_a, a_cid + 4u * c0, a_stage + 4u * excl);
           expand_hits(mask_b, a_id + 4u * sa, p);
@@ -597,6 +602,7 @@ __global__ void __launch_bounds__(kPlaceThreads, 2) bin_place_kernel(const Binne
     s_off[s] = 0;
   }
   __syncthreads();
+  BCU_DEV_ASSERT(n_live <= n_here && n_here <= (uint32_t)kTileQ);
   for (uint32_t s = tid; s < n_live; s += kPlaceThreads) s_off[s_loc[s]] = sres[s].y;  // counts by query position
   __syncthreads();
   // exclusive scan over the tile's 4096 counts (kPlaceQPT consecutive entries per thread)
@@ -647,6 +653,7 @@ __global__ void __launch_bounds__(kPlaceThreads, 2) bin_place_kernel(const Binne
 #pragma unroll
         for (uint32_t u = 0; u < 4; ++u) {
           const uint64_t d = dst0 + j0 + u - w0;  // wraps far above the window for ids that lie before it
+          BCU_DEV_ASSERT(!(j0 + u < cnt && stored) || (uint64_t)r.x + j0 + u < a.stage_cap);
           if (j0 + u < cnt && d < (uint64_t)kPlaceCap) s_out[d] = v[u];
         }
       }

@@ -37,6 +37,23 @@ extern std::atomic<uint64_t> g_launches;
     BCU_CUDA(cudaGetLastError());                       \
   } while (0)
 
+// Device-side bounds assertions. compute-sanitizer is closed on this GPU pool, so memory safety is checked by a
+// second build of the library (make check -> libbinary_cuda_check.so, -DBCU_BOUNDS_CHECK) whose kernels trap on any
+// index outside the extent of the array it addresses; tests/test_gpu_bounds.py runs the parity shapes through it.
+#ifdef BCU_BOUNDS_CHECK
+#define BCU_DEV_ASSERT(cond)                                                        \
+  do {                                                                              \
+    if (!(cond)) {                                                                  \
+      printf("BCU_BOUNDS_CHECK failed: %s:%d: %s\n", __FILE__, __LINE__, #cond);    \
+      __trap();                                                                     \
+    }                                                                               \
+  } while (0)
+#else
+#define BCU_DEV_ASSERT(cond) \
+  do {                       \
+  } while (0)
+#endif
+
 // RAII guard: make `device` current for the scope, restore on exit.
 struct DeviceGuard {
   int prev = -1;

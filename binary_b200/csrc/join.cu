@@ -68,6 +68,9 @@ struct JoinArgs {
   const uint32_t* __restrict__ hs;    // each segment's `high` values ascending (O(1) long-range count)
   const uint32_t* __restrict__ dirh;  // per directory entry: first index of hs with value >= b*W
   const GroupDesc* __restrict__ groups;
+  uint64_t n_rows;  // extents, for the bounds-checked build: rows of the index (arrays are padded by 4),
+  uint64_t n_dir;   // directory entries,
+  uint64_t n_state; // entries of the probe state arrays / of the long-range list
   uint32_t n_groups;
   uint32_t shifts;  // bin shift of length-class slot c in byte c
   uint32_t max_gval;
@@ -267,9 +270,11 @@ __device__ __forceinline__ void query_bounds(const JoinArgs& a, const GroupTable
     uint32_t b_hi = qh >> shift;
     if (b_hi >= nb) b_hi = nb - 1u;
     // {lb(b_lo), ub(b_lo + 1), row lb}: all a one-bin query with one candidate needs
+    BCU_DEV_ASSERT(bin_base + b_hi < a.n_dir && b_lo < nb);
     const uint4 e = ldg_u4(reinterpret_cast<const uint4*>(a.dir + bin_base + b_lo));
     uint32_t u = e.y;
     if (b_hi != b_lo) u = a.dir[bin_base + b_hi].ub;
+    BCU_DEV_ASSERT(e.x <= a.n_rows && u <= a.n_rows);
     lb = e.x;
     len = u > e.x ? u - e.x : 0u;
     inline_mask = (uint32_t)(len > 0 && accept<FILT>(a.filter_kind, a.filter_diff, a.filter_use_strand, strand,
@@ -300,6 +305,7 @@ __device__ __forceinline__ void scan_short(const JoinArgs& a, const uint32_t (&q
 #pragma unroll
     for (int j = 0; j < kQPT; ++j) {
       t[j] = make_uint2(0xffffffffu, 0u);
+      BCU_DEV_ASSERT(k >= n[j] || (uint64_t)lb[j] + k < a.n_rows);
       if (k < n[j]) t[j] = ldg_u2(a.lowhigh + lb[j] + k);
     }
 #pragma unroll
@@ -328,6 +334,7 @@ struct LongCtx {  // what the long-range path needs, passed BY VALUE into the ou
   uint32_t qid_base;
   uint32_t comp_shift;
   uint32_t filter_kind, filter_diff, filter_use_strand;
+  uint64_t n_rows;
 };
 
 struct LongRange {
@@ -341,6 +348,7 @@ struct LongRange {
 __device__ __forceinline__ uint32_t exact_upper_bound(const JoinArgs& a, uint32_t lb, uint32_t len,
                                                       uint32_t qh) {
   uint32_t u = lb + len;
+  BCU_DEV_ASSERT((uint64_t)lb + len <= a.n_rows);
   while (u > lb && a.lowhigh[u - 1].x > qh) --u;
   return u;
 }
@@ -375,6 +383,7 @@ __device__ __forceinline__ uint32_t count_by_ranks(const JoinArgs& a, const Grou
   if (!proper) return kNoRank;
   const uint64_t bin_base = in_smem ? tb.g_base[gi] : a.groups[gi].bin_base;
   const uint32_t row_end = in_smem ? tb.g_re[gi] : a.groups[gi].row_end;
+  BCU_DEV_ASSERT(bin_base + (ql >> slot_shift(a, slot)) < a.n_dir && row_end <= a.n_rows);
   uint32_t i = a.dirh[bin_base + (ql >> slot_shift(a, slot))];  // b_lo < nb: the range is non-empty
   while (i < row_end && a.hs[i] < ql) ++i;
   return ub_exact > i ? ub_exact - i : 0u;
@@ -400,6 +409,7 @@ __device__ __forceinline__ uint32_t count_long(const LongCtx& c, int lane, const
   for (uint32_t r = (R.lb & ~3u) + 4u * lane; (r - 4u * lane) < R.ub; r += 256) {
     const uint32_t r2 = r + 128;
     uint4 h0 = make_uint4(0, 0, 0, 0), h1 = make_uint4(0, 0, 0, 0);
+    BCU_DEV_ASSERT(R.ub <= c.n_rows);  // a 128-bit load may reach up to 3 rows past ub: the arrays are padded by 4
     if (r < R.ub) h0 = ldg_u4(high4 + (r >> 2));
     if (r2 < R.ub) h1 = ldg_u4(high4 + (r2 >> 2));
     count += __popc(rows_in_range(r, R.lb, R.ub) & reaches(R.ql, h0));
@@ -427,6 +437,7 @@ __device__ __forceinline__ void long_preload(const LongCtx& c, int lane, const L
     g.hi[t] = 0;
     g.lo[t] = 0xffffffffu;
     g.id[t] = 0;
+    BCU_DEV_ASSERT(R.ub <= c.n_rows);
     if (r < R.ub) {
       if (FILT) {
         const uint2 v = ldg_u2(c.lowhigh + r);
@@ -458,6 +469,7 @@ __device__ __forceinline__ void long_consume(const LongCtx& c, int lane, const L
     } else {
       const unsigned bal = __ballot_sync(0xffffffffu, hit);
       const uint32_t p = count + __popc(bal & lt);
+      BCU_DEV_ASSERT(!(hit && p < lim) || R.base + p < c.capacity);
       if (hit && p < lim) out[p] = g.id[t];
       count += __popc(bal);
     }
@@ -556,6 +568,7 @@ __device__ __forceinline__ LongCtx long_ctx(const JoinArgs& a) {
   c.filter_kind = a.filter_kind;
   c.filter_diff = a.filter_diff;
   c.filter_use_strand = a.filter_use_strand;
+  c.n_rows = a.n_rows;
   return c;
 }
 __device__ __forceinline__ uint32_t pack_bits(const bool (&b)[kQPT]) {
@@ -621,6 +634,7 @@ __device__ __forceinline__ void emit_short(const JoinArgs& a, StageBuffers& st, 
         id[t] = 0;
         if (s < n_here) {
           v[t] = st.vq[warp][s];
+          BCU_DEV_ASSERT(v[t].x < a.n_rows);
           id[t] = __ldg(a.ids + v[t].x);
         }
       }
@@ -711,6 +725,7 @@ __global__ void __launch_bounds__(kJoinThreads, kProbeMinBlocks) probe_kernel(co
 #pragma unroll
         for (int j = 0; j < kQPT; ++j)
           if (big[j]) {
+            BCU_DEV_ASSERT(chunk_begin + base < a.n_state && q0 + j < a.n_state);
             list[base++] = q0 + j;
             a.st_ub[q0 + j] = ub[j];
             w[j] = kBigFlag;
@@ -732,6 +747,7 @@ __global__ void __launch_bounds__(kJoinThreads, kProbeMinBlocks) probe_kernel(co
       }
     }
     // state: 8 bytes per query, 128-bit stores (the arrays are padded to a multiple of kCtaTile)
+    BCU_DEV_ASSERT((uint64_t)q0 + kQPT <= a.n_state);
     *reinterpret_cast<uint4*>(a.st_lb + q0) = make_uint4(lb[0], lb[1], lb[2], lb[3]);
     *reinterpret_cast<uint4*>(a.st_w + q0) = make_uint4(w[0], w[1], w[2], w[3]);
   }
@@ -1134,6 +1150,9 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
   a.hs = ix->d_hs;
   a.dirh = ix->d_dirh;
   a.groups = ix->d_groups;
+  a.n_rows = ix->n;
+  a.n_dir = ix->n_bins;
+  a.n_state = 0;
   a.n_groups = ix->n_groups;
   a.shifts = ix->shifts;
   a.max_gval = ix->max_gval;
@@ -1211,6 +1230,7 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
   a.st_ub = a.st_w + padded;
   a.big_list = a.st_ub + padded;
   a.cta_big = a.big_list + padded;
+  a.n_state = padded;
   if (filt) probe_kernel<true><<<grid, kJoinThreads, 0, stream>>>(a);
   else probe_kernel<false><<<grid, kJoinThreads, 0, stream>>>(a);
   BCU_LAUNCHED();

@@ -141,3 +141,50 @@ def write_synth_vcfs(directory, seed=1, n_sv=3000, n_nl=2000):
     with gzip.open(sv_path, "wt") as fh:
         fh.write("\n".join(head + sv_lines) + "\n")
     return nl_path, sv_path
+
+
+def write_config_e_vcfs(directory, n_sv=1_000_000, n_nl=5_000_000):
+    """BASELINE.json configs[4] ("E"): a synthetic delly-style SV VCF (DUP/INV/BND) and a ScanNLS-style NL VCF
+    (TDUP/INV/TRA) with the hg38 chromosome law and config B's length law, as VCF text. Returns (nl_path, sv_path)."""
+    import os
+    from binary_b200 import synth
+    names = np.array(synth.HG38_NAMES, dtype=object)
+    head = ["##fileformat=VCFv4.2"] + [f"##contig=<ID={n},length={l}>" for n, l in synth.HG38] + VCF_INFO_HEADER + \
+           ["#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO"]
+
+    def write(path, seed, n, kinds, probs, end_key, nls):
+        g, lo, hi = synth.intervals_mt(seed, 0, n, "loguniform", 50, 10_000)
+        rng = np.random.default_rng(seed)
+        kind = rng.choice(np.array(kinds, dtype=object), size=n, p=probs)
+        chr2 = names[rng.integers(0, 24, n)]
+        pos2 = rng.integers(1, 40_000_000, n)
+        s1 = rng.choice(np.array(["+", "-"], dtype=object), n)
+        s2 = rng.choice(np.array(["+", "-"], dtype=object), n)
+        with open(path, "w") as fh:
+            fh.write("\n".join(head) + "\n")
+            for b in range(0, n, 500_000):
+                out = []
+                for i in range(b, min(n, b + 500_000)):
+                    k, c = kind[i], names[g[i]]
+                    if k in ("BND", "TRA"):
+                        info = f"SVTYPE={k};CHR2={chr2[i]};" + (f"POS2={pos2[i]}" if k == "BND" else f"SVEND={pos2[i]}")
+                    else:
+                        info = f"SVTYPE={k};{end_key}={hi[i] + 1}"
+                        if nls:
+                            info += f";STRAND1={s1[i]};STRAND2={s2[i]}"
+                    out.append(f"{c}\t{lo[i] + 1}\tr{i}\tN\t<{k}>\t.\t.\t{info}")
+                fh.write("\n".join(out) + "\n")
+
+    sv_path, nl_path = os.path.join(directory, "sv.vcf"), os.path.join(directory, "nl.vcf")
+    write(sv_path, 0xE5A0, n_sv, ["DUP", "INV", "BND"], [0.5, 0.25, 0.25], "END", False)
+    write(nl_path, 0xE5A1, n_nl, ["TDUP", "INV", "TRA"], [0.5, 0.25, 0.25], "SVEND", True)
+    return nl_path, sv_path
+
+
+def line_set_digest(lines):
+    """(count, order-independent 64-bit hash) of a list of text lines: sum of the first 8 bytes of blake2b(line)."""
+    import hashlib
+    h = 0
+    for l in lines:
+        h = (h + int.from_bytes(hashlib.blake2b(l.encode(), digest_size=8).digest(), "little")) & 0xFFFFFFFFFFFFFFFF
+    return len(lines), h
