@@ -61,7 +61,7 @@ struct BinnedArgs {
   const GroupDesc* __restrict__ gtable;  // [n_cls][n_groups] (general index: used by the spill path)
   const BinDesc* __restrict__ desc;
   const BinGroup* __restrict__ groups;
-  const uint16_t* __restrict__ cell2bin;
+  const uint32_t* __restrict__ cellbits;  // [2 * ceil(n_cells / 32)]: first-cell-of-a-bin bits, then their rank per word
   uint32_t n_groups, n_bins, n_cells, cell_shift, max_gval, n_cls;
   // batch
   const uint32_t* __restrict__ qgroup;
@@ -91,7 +91,7 @@ struct BinnedArgs {
   uint64_t* total_mapped;
   uint32_t qid_base;
   int emit;          // 0 = offsets only (count mode)
-  int ht_aligned;    // hit_target is 16-byte aligned (vector stores)
+  int ht_aligned, hq_aligned;  // the pair columns are 16-byte aligned (vector stores)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -151,7 +151,7 @@ __device__ __forceinline__ int run_owner(uint32_t incl, uint32_t f) {
 // this kernel's time). With more than kSortMaxWarpHistBins bins the per-warp histograms do not fit and
 // shared-memory atomics are used instead.
 // Dynamic shared memory: rec[kTileQ] uint2 | hist[K + 2] u32 | groups[n_groups] BinGroup | loc[kTileQ] u16 |
-// cell2bin[n_cells] u16 | gmap[kBnDirectGroups] u16 | whist[kSortWarps][K + 2] u16 (WARP_HIST only)
+// cellbits[2 * ceil(n_cells / 32)] u32 | gmap[kBnDirectGroups] u16 | whist[kSortWarps][K + 2] u16 (WARP_HIST only)
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr uint32_t kSortMaxWarpHistBins = 2046;
 
@@ -164,14 +164,15 @@ __global__ void __launch_bounds__(kSortThreads, 2) bin_sort_kernel(const BinnedA
   uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_rec + kTileQ);
   BinGroup* s_grp = reinterpret_cast<BinGroup*>(s_hist + Kp);
   uint16_t* s_loc = reinterpret_cast<uint16_t*>(s_grp + a.n_groups);
-  uint16_t* s_c2b = s_loc + kTileQ;
-  uint16_t* s_gmap = s_c2b + ((a.n_cells + 7) & ~7u);
+  const uint32_t n_words = (a.n_cells + 31) / 32;
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_loc + kTileQ);  // [n_words] bits, [n_words] ranks
+  uint16_t* s_gmap = reinterpret_cast<uint16_t*>(s_bits + ((2 * n_words + 3) & ~3u));
   uint16_t* s_whist = s_gmap + kBnDirectGroups;  // [kSortWarps][Kp]
   __shared__ uint64_t s_scan[kSortThreads / 32 + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool direct = a.max_gval < (uint32_t)kBnDirectGroups;
 
-  for (uint32_t i = tid; i < a.n_cells; i += kSortThreads) s_c2b[i] = a.cell2bin[i];
+  for (uint32_t i = tid; i < 2 * n_words; i += kSortThreads) s_bits[i] = a.cellbits[i];
   for (uint32_t i = tid; i < a.n_groups; i += kSortThreads) s_grp[i] = a.groups[i];
   if (direct)
     for (int i = tid; i < kBnDirectGroups; i += kSortThreads) s_gmap[i] = 0xffffu;
@@ -220,14 +221,22 @@ __global__ void __launch_bounds__(kSortThreads, 2) bin_sort_kernel(const BinnedA
         bin[j] = K;
         if (gi != 0xffffu) {
           const uint32_t cell = ql[j] >> a.cell_shift;
-          if (cell < s_grp[gi].n_cells) {
-            const uint32_t b = s_c2b[s_grp[gi].cell_base + cell];
-            if (b != kBinNull) bin[j] = b;
+          if (cell < s_grp[gi].n_cells) {  // bin = (number of bins that begin at or before the cell) - 1
+            const uint32_t c = s_grp[gi].cell_base + cell;
+            bin[j] = s_bits[n_words + (c >> 5)] + __popc(s_bits[c >> 5] & (0xffffffffu >> (31u - (c & 31u)))) - 1u;
           }
         }
       }
-      if (WARP_HIST) {
-        const unsigned peers = __match_any_sync(0xffffffffu, bin[j]);  // lanes of this warp holding the same bin
+    }
+    // ranks: the eight match.any of a lane are independent and are issued together; the counter updates that use
+    // them are a read-modify-write per round (plain shared-memory accesses inside one warp)
+    if (WARP_HIST) {
+      unsigned peers_of[kSortQPT];
+#pragma unroll
+      for (int j = 0; j < kSortQPT; ++j) peers_of[j] = __match_any_sync(0xffffffffu, bin[j]);
+#pragma unroll
+      for (int j = 0; j < kSortQPT; ++j) {
+        const unsigned peers = peers_of[j];
         const uint32_t before = __popc(peers & ((1u << lane) - 1u));
         uint16_t* cnt = s_whist + warp * Kp + bin[j];
         const uint32_t h = *cnt;
@@ -235,9 +244,10 @@ __global__ void __launch_bounds__(kSortThreads, 2) bin_sort_kernel(const BinnedA
         if (before == 0) *cnt = (uint16_t)(h + __popc(peers));
         __syncwarp();
         rank[j] = h + before;
-      } else {
-        rank[j] = bin[j] <= K ? atomicAdd(&s_hist[bin[j]], 1u) : 0u;
       }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kSortQPT; ++j) rank[j] = bin[j] <= K ? atomicAdd(&s_hist[bin[j]], 1u) : 0u;
     }
     __syncthreads();
     if (WARP_HIST)  // per bin: counts of the warps -> exclusive prefix over the warps, total into hist
@@ -343,16 +353,27 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
-// hit mask of the w <= 32 candidates whose `high` values start at shared address `addr`: bit j = (high[j] >= ql)
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+// hit mask of the w <= 32 candidates whose `high` values start at shared address `addr`: bit j = (high[j] >= ql).
+// Four candidates per 128-bit load from the 16-byte row the window starts in (the rows before the window are
+// shifted out at the end; the arrays begin on a row and are followed by other arrays of the tile, so the first and
+// the last load stay inside it).
 __device__ __forceinline__ uint32_t window_mask(uint32_t addr, uint32_t w, uint32_t ql) {
-  uint32_t mask = 0;
-  uint32_t j = 0;
-  for (; j + 2 <= w; j += 2) {  // two loads in flight
-    const uint32_t v0 = lds32(addr + 4u * j), v1 = lds32(addr + 4u * j + 4u);
-    mask |= ((uint32_t)(v0 >= ql) | ((uint32_t)(v1 >= ql) << 1)) << j;
+  if (w == 0) return 0u;
+  const uint32_t skip = (addr >> 2) & 3u;
+  uint32_t row = addr & ~15u;
+  uint64_t acc = 0;
+  for (uint32_t k = 0; k < skip + w; k += 4, row += 16u) {
+    const uint4 v = lds128(row);
+    const uint32_t b = (uint32_t)(v.x >= ql) | ((uint32_t)(v.y >= ql) << 1) | ((uint32_t)(v.z >= ql) << 2) |
+                       ((uint32_t)(v.w >= ql) << 3);
+    acc |= (uint64_t)b << k;
   }
-  if (j < w) mask |= (uint32_t)(lds32(addr + 4u * j) >= ql) << j;
-  return mask;
+  return (uint32_t)(acc >> skip) & (w >= 32u ? 0xffffffffu : (1u << w) - 1u);
 }
 
 // the ids of the hits in `mask` (candidate j -> shared word ids + 4j) are appended at shared address `out`
@@ -631,7 +652,24 @@ __global__ void __launch_bounds__(kPlaceThreads, 2) bin_place_kernel(const Binne
   if (!EMIT) return;
 
   const uint64_t total = tile_total;
+  // window position p lives in s_out[p + shift], shift = (first output position of the window) mod 4, so that
+  // 16-byte rows of shared memory line up with 16-byte rows of the output columns
+  auto write_out = [&](uint32_t* __restrict__ col, bool aligned, uint64_t first, uint32_t shift, uint32_t n_out) {
+    const uint64_t row0 = first - shift;  // multiple of 4
+    const uint32_t end = n_out + shift;
+    for (uint32_t p4 = tid * 4; p4 < end; p4 += kPlaceThreads * 4) {
+      const uint64_t pos = row0 + p4;
+      if (aligned && p4 >= shift && p4 + 4 <= end && pos + 4 <= a.capacity) {
+        *reinterpret_cast<uint4*>(col + pos) = *reinterpret_cast<const uint4*>(s_out + p4);
+      } else {
+#pragma unroll
+        for (uint32_t u = 0; u < 4; ++u)
+          if (p4 + u >= shift && p4 + u < end && pos + u < a.capacity) col[pos + u] = s_out[p4 + u];
+      }
+    }
+  };
   for (uint64_t w0 = 0; w0 < total; w0 += kPlaceCap) {
+    const uint32_t shift = (uint32_t)((base + w0) & 3u);
     // gather: a lane per slot copies its own id list (the lists of neighbouring slots lie next to each other in
     // the staging area, so the lanes of a warp read the same few sectors; four loads are issued before the stores).
     // Measured against warp-cooperative copies of the flattened lists (owner of every id by shuffle search, or by
@@ -641,41 +679,42 @@ __global__ void __launch_bounds__(kPlaceThreads, 2) bin_place_kernel(const Binne
       uint2 r = make_uint2(0u, 0u);
       uint64_t dst0 = 0;
       if (s < n_live) { r = sres[s]; dst0 = s_off[s_loc[s]]; }
-      const bool touches = r.y != 0 && dst0 < w0 + kPlaceCap && dst0 + r.y > w0;
-      const uint32_t cnt = touches ? r.y : 0u;
-      const uint32_t steps = __reduce_max_sync(0xffffffffu, cnt);
-      const uint32_t* src = a.staging + r.x;
+      // the part [j_lo, j_hi) of the list that falls into the window, once, in 64 bits; the copy loop is 32-bit
+      const uint64_t w1 = w0 + kPlaceCap;
+      const uint32_t j_lo = dst0 >= w0 ? 0u : (uint32_t)min((uint64_t)r.y, w0 - dst0);
+      const uint32_t j_hi = w1 > dst0 ? (uint32_t)min((uint64_t)r.y, w1 - dst0) : 0u;
+      const uint32_t n = j_hi > j_lo ? j_hi - j_lo : 0u;
+      const uint32_t steps = __reduce_max_sync(0xffffffffu, n);
+      if (steps == 0) continue;
       const bool stored = r.x != kNotStored;
+      BCU_DEV_ASSERT(!(n && stored) || (uint64_t)r.x + j_hi <= a.stage_cap);
+      const uint32_t* sp = a.staging + r.x + j_lo;
+      uint32_t* op = s_out + shift + (uint32_t)(dst0 + j_lo - w0);
       for (uint32_t j0 = 0; j0 < steps; j0 += 4) {
         uint32_t v[4];
 #pragma unroll
-        for (uint32_t u = 0; u < 4; ++u) v[u] = (j0 + u < cnt && stored) ? src[j0 + u] : kNotStored;
+        for (uint32_t u = 0; u < 4; ++u) v[u] = (j0 + u < n && stored) ? sp[j0 + u] : kNotStored;
 #pragma unroll
-        for (uint32_t u = 0; u < 4; ++u) {
-          const uint64_t d = dst0 + j0 + u - w0;  // wraps far above the window for ids that lie before it
-          BCU_DEV_ASSERT(!(j0 + u < cnt && stored) || (uint64_t)r.x + j0 + u < a.stage_cap);
-          if (j0 + u < cnt && d < (uint64_t)kPlaceCap) s_out[d] = v[u];
-        }
+        for (uint32_t u = 0; u < 4; ++u)
+          if (j0 + u < n) op[j0 + u] = v[u];
       }
     }
     __syncthreads();
     const uint32_t n_out = (uint32_t)min((uint64_t)kPlaceCap, total - w0);
-    for (uint32_t p = tid; p < n_out; p += kPlaceThreads) {
-      const uint64_t pos = base + w0 + p;
-      if (pos < a.capacity) a.hit_target[pos] = s_out[p];
-    }
+    write_out(a.hit_target, a.ht_aligned != 0, base + w0, shift, n_out);
     __syncthreads();
     if (a.hit_query) {  // the query-id column: every query fills its own stretch of the window
       for (uint32_t i = tid; i < n_here; i += kPlaceThreads) {
         const uint64_t b = max(s_off[i], w0), e = min(s_off[i + 1], w0 + (uint64_t)kPlaceCap);
         const uint32_t qid = a.qid_base + (uint32_t)(q0 + i);
-        for (uint64_t p = b; p < e; ++p) s_out[p - w0] = qid;
+        if (e > b) {
+          uint32_t* op = s_out + shift + (uint32_t)(b - w0);
+          const uint32_t n = (uint32_t)(e - b);
+          for (uint32_t p = 0; p < n; ++p) op[p] = qid;
+        }
       }
       __syncthreads();
-      for (uint32_t p = tid; p < n_out; p += kPlaceThreads) {
-        const uint64_t pos = base + w0 + p;
-        if (pos < a.capacity) a.hit_query[pos] = s_out[p];
-      }
+      write_out(a.hit_query, a.hq_aligned != 0, base + w0, shift, n_out);
       __syncthreads();
     }
   }
@@ -713,7 +752,7 @@ int launch_join_binned(const bcu_index* ix, int mode, uint64_t n_q, const uint32
   BinnedArgs a;
   a.low = ix->d_bn_low; a.high = ix->d_bn_high; a.ids = ix->d_bn_id; a.blob = ix->d_bn_blob;
   a.lowhigh = ix->d_lowhigh; a.gids = ix->d_id; a.dir = ix->d_dir;
-  a.gtable = ix->d_groups; a.desc = ix->d_bn_desc; a.groups = ix->d_bn_groups; a.cell2bin = ix->d_bn_cell2bin;
+  a.gtable = ix->d_groups; a.desc = ix->d_bn_desc; a.groups = ix->d_bn_groups; a.cellbits = ix->d_bn_cellbits;
   a.n_groups = ix->n_groups; a.n_bins = ix->bn_bins; a.n_cells = ix->bn_cells; a.cell_shift = ix->bn_cell_shift;
   a.max_gval = ix->max_gval; a.n_cls = ix->n_comp;
   a.qgroup = d_qgroup; a.qlow = d_qlow; a.qhigh = d_qhigh; a.n_q = (uint32_t)n_q; a.n_tiles = (uint32_t)n_tiles;
@@ -721,6 +760,7 @@ int launch_join_binned(const bcu_index* ix, int mode, uint64_t n_q, const uint32
   a.total = d_total; a.total_mapped = total_mapped; a.qid_base = query_id_base; a.emit = emit;
   a.stage_cap = stage_cap;
   a.ht_aligned = (reinterpret_cast<uintptr_t>(d_hit_target) & 15u) == 0;
+  a.hq_aligned = (reinterpret_cast<uintptr_t>(d_hit_query) & 15u) == 0;
 
   // one stream-ordered allocation, carved up (every piece 256-byte aligned)
   const uint32_t K = ix->bn_bins;
@@ -753,7 +793,7 @@ int launch_join_binned(const bcu_index* ix, int mode, uint64_t n_q, const uint32
 
   const bool warp_hist = K <= kSortMaxWarpHistBins;
   const size_t sort_smem = (size_t)kTileQ * 8 + (size_t)((K + 2 + 3) & ~3u) * 4 + (size_t)ix->n_groups * sizeof(BinGroup) +
-                           (size_t)kTileQ * 2 + (size_t)((ix->bn_cells + 7) & ~7u) * 2 + (size_t)kBnDirectGroups * 2 +
+                           (size_t)kTileQ * 2 + (size_t)((2 * ((ix->bn_cells + 31) / 32) + 3) & ~3u) * 4 + (size_t)kBnDirectGroups * 2 +
                            (warp_hist ? (size_t)kSortWarps * ((K + 2 + 3) & ~3u) * 2 : 0);
   const size_t probe_smem = (size_t)kBinTileBytes + (size_t)kProbeWarps * kStageIds * 4;
   const size_t place_smem = (size_t)(kTileQ + 2) * 8 + (size_t)(kPlaceCap + 4) * 4 + (size_t)kTileQ * 2;

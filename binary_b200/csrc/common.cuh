@@ -165,7 +165,9 @@ struct bcu_index {
   unsigned char* d_bn_blob = nullptr;  // per bin: sub-cell tables + coverage lists (BinDesc::blob)
   bcu::BinDesc* d_bn_desc = nullptr;   // [bn_bins]
   bcu::BinGroup* d_bn_groups = nullptr;  // [n_groups]
-  uint16_t* d_bn_cell2bin = nullptr;   // [bn_cells]
+  uint16_t* d_bn_cell2bin = nullptr;   // [bn_cells] (used while building the coverage lists)
+  uint32_t* d_bn_cellbits = nullptr;   // [2 * ceil(bn_cells / 32)] routing table of the sort kernel: bit i = cell i is the
+                                       // first cell of a bin, then the number of such bits before every word
 };
 
 namespace bcu {

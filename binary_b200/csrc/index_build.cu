@@ -247,8 +247,10 @@ static void free_bin_layout(bcu_index* ix) {
   cudaFreeAsync(ix->d_bn_desc, nullptr);
   cudaFreeAsync(ix->d_bn_groups, nullptr);
   cudaFreeAsync(ix->d_bn_cell2bin, nullptr);
+  cudaFreeAsync(ix->d_bn_cellbits, nullptr);
   cudaFreeAsync(ix->d_bn_blob, nullptr);
   ix->d_bn_desc = nullptr; ix->d_bn_groups = nullptr; ix->d_bn_cell2bin = nullptr; ix->d_bn_blob = nullptr;
+  ix->d_bn_cellbits = nullptr;
   ix->bn_bins = 0;
   cudaGetLastError();
 }
@@ -274,6 +276,7 @@ static void free_index_members(bcu_index* ix) {
   cudaFreeAsync(ix->d_bn_desc, nullptr);
   cudaFreeAsync(ix->d_bn_groups, nullptr);
   cudaFreeAsync(ix->d_bn_cell2bin, nullptr);
+  cudaFreeAsync(ix->d_bn_cellbits, nullptr);
   cudaFreeAsync(ix->d_bn_blob, nullptr);
   cudaGetLastError();
 }
@@ -720,8 +723,8 @@ __global__ void gather_u32_kernel(const uint32_t* __restrict__ src, const uint32
 // One attempt with a given row target per bin. *too_big is set when a bin's rows + blob exceed the tile: the
 // caller retries with a smaller target.
 static int bin_layout_attempt(bcu_index* ix, const uint32_t* group_gval, const uint32_t* group_begin_h,
-                              const uint32_t* group_cmax, cudaStream_t stream, uint32_t rows_target, bool* too_big) {
-  *too_big = false;
+                              const uint32_t* group_cmax, cudaStream_t stream, uint32_t rows_target, double* too_big) {
+  *too_big = 0.0;  // on return: by what factor the largest bin exceeds the tile (0 = every bin fits)
   const uint32_t G = ix->n_groups, n = (uint32_t)ix->n;
   // cell width: the routing table over all groups must stay within kBinMaxCells entries
   uint32_t shift = 0;
@@ -809,6 +812,15 @@ static int bin_layout_attempt(bcu_index* ix, const uint32_t* group_gval, const u
   BCU_CUDA(cudaMemcpyAsync(ix->d_bn_desc, bins.data(), (size_t)K * sizeof(BinDesc), cudaMemcpyHostToDevice, stream));
   BCU_CUDA(cudaMemcpyAsync(ix->d_bn_groups, groups.data(), (size_t)G * sizeof(BinGroup), cudaMemcpyHostToDevice, stream));
   BCU_CUDA(cudaMemcpyAsync(ix->d_bn_cell2bin, cell2bin.data(), (size_t)n_cells * 2, cudaMemcpyHostToDevice, stream));
+  // the same map as a rank structure (bins are numbered in cell order): 1/10 of the bytes, which is what lets
+  // two CTAs of the routing kernel share an SM
+  const uint32_t n_words = (n_cells + 31) / 32;
+  std::vector<uint32_t> cellbits(2 * (size_t)n_words, 0u);
+  for (uint32_t i = 0; i < n_cells; ++i)
+    if (i == 0 || cell2bin[i] != cell2bin[i - 1]) cellbits[i >> 5] |= 1u << (i & 31);
+  for (uint32_t w = 1; w < n_words; ++w) cellbits[n_words + w] = cellbits[n_words + w - 1] + (uint32_t)__builtin_popcount(cellbits[w - 1]);
+  BCU_CUDA(cudaMallocAsync((void**)&ix->d_bn_cellbits, cellbits.size() * 4, stream));
+  BCU_CUDA(cudaMemcpyAsync(ix->d_bn_cellbits, cellbits.data(), cellbits.size() * 4, cudaMemcpyHostToDevice, stream));
   uint32_t *d_sub_base, *d_sub_start, *d_cnt, *d_off, *d_bin_off;
   unsigned long long* d_total;
   BCU_CUDA(tmp.alloc(&d_sub_base, K + 1));
@@ -850,11 +862,12 @@ static int bin_layout_attempt(bcu_index* ix, const uint32_t* group_gval, const u
     d.blob = blob_bytes;
     d.blob_bytes = ((d.nsub + 1 + 7) & ~7u) * 4u + d.n_cov * 8u;
     blob_bytes += d.blob_bytes;
-    if (d.n_cov > 65535u || (uint64_t)d.n_copy * 12u + d.blob_bytes > kBinTileBytes) {
-      free_bin_layout(ix);
-      *too_big = true;
-      return BCU_OK;
-    }
+    const double over = std::max((double)d.n_cov / 65535.0, ((double)d.n_copy * 12.0 + d.blob_bytes) / (double)kBinTileBytes);
+    if (over > 1.0) *too_big = std::max(*too_big, over);
+  }
+  if (*too_big > 0.0) {
+    free_bin_layout(ix);
+    return BCU_OK;
   }
   uint32_t* d_cursor;
   BCU_CUDA(tmp.alloc(&d_cursor, (uint64_t)n_slots + 4));
@@ -886,11 +899,11 @@ int build_bin_layout(bcu_index* ix, const uint32_t* group_gval, const uint32_t* 
   // the coverage lists of a bin are only known after they are counted: start from a target that leaves them a
   // third of the tile and shrink it while some bin does not fit
   uint32_t rows_target = (uint32_t)std::max(16.0, std::min(12288.0, env_double("BCU_BIN_ROWS", 8192.0)));
-  for (int attempt = 0; attempt < 4; ++attempt) {
-    bool too_big = false;
-    BCU_TRY(bin_layout_attempt(ix, group_gval, group_begin_h, group_cmax, stream, rows_target, &too_big));
-    if (!too_big) break;
-    rows_target = rows_target * 2 / 3;
+  for (int attempt = 0; attempt < 5; ++attempt) {
+    double over = 0.0;
+    BCU_TRY(bin_layout_attempt(ix, group_gval, group_begin_h, group_cmax, stream, rows_target, &over));
+    if (over == 0.0) break;
+    rows_target = (uint32_t)((double)rows_target / over * 0.96);  // the fullest bin decides, with a little room
     if (rows_target < 16) break;
   }
   return BCU_OK;
