@@ -593,6 +593,17 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
     for (uint32_t g = 0; g < n_groups; ++g)
       bn_cmax[g] = (uint32_t)std::min<uint64_t>(((((uint64_t)bn_cmax[g] >> class_shift[0]) + 1) << class_shift[0]) - 1, 0xffffffffull);
   BCU_TRY(build_bin_layout(ix, gval.data(), bn_begin.data(), bn_cmax.data(), stream));
+  if (ix->bn_bins == 0) {  // no layout: the (group, low)-sorted copies are not needed
+    cudaFreeAsync(ix->d_bn_low, stream);
+    ix->bytes -= n * 4;
+    if (ix->bn_owns_rows) {
+      cudaFreeAsync(ix->d_bn_high, stream);
+      cudaFreeAsync(ix->d_bn_id, stream);
+      ix->bytes -= n * 8;
+    }
+    ix->d_bn_low = ix->d_bn_high = ix->d_bn_id = nullptr;
+    ix->bn_owns_rows = false;
+  }
   mark("bin layout");
   return BCU_OK;
 }
@@ -896,6 +907,10 @@ int build_bin_layout(bcu_index* ix, const uint32_t* group_gval, const uint32_t* 
   const char* off_env = std::getenv("BCU_BINNED");
   if (ix->n == 0 || ix->n_groups == 0 || ix->n_groups > (uint32_t)kMaxSmemGroups || (off_env && off_env[0] == '0'))
     return BCU_OK;
+  // The binned path only pays for indexes far beyond L2 (launch_join_binned: >= 96 MB): smaller ones skip the
+  // layout and its build time (BCU_BINNED=1 builds it regardless -- tests, experiments)
+  const bool forced = off_env && off_env[0] == '1';
+  if (!forced && (double)ix->n < env_double("BCU_BINNED_MIN_TARGETS", 2.0e6)) return BCU_OK;
   // the coverage lists of a bin are only known after they are counted: start from a target that leaves them a
   // third of the tile and shrink it while some bin does not fit
   uint32_t rows_target = (uint32_t)std::max(16.0, std::min(12288.0, env_double("BCU_BIN_ROWS", 8192.0)));

@@ -146,8 +146,9 @@ def test_binned_equals_general_path_on_the_same_index(port_oracle):
     rebuilds its bin layout."""
     import torch
     c = random_case(41, n_t=50000, n_q=30000, n_groups=6, span=5_000_000, max_len=3000, long_frac=0.001)
-    with env(BCU_BIN_ROWS=2048):
+    with env(BCU_BINNED=1, BCU_BIN_ROWS=2048):
         ix = DeviceIndex.build(c["tl"], c["th"], c["tg"])
+    assert ix.info()["binned_tiles"] > 0
     with env(BCU_BINNED=0):
         off0, hq0, ht0 = dev_join(ix, c["ql"], c["qh"], c["qg"])
     with env(BCU_BINNED=1):
@@ -158,7 +159,7 @@ def test_binned_equals_general_path_on_the_same_index(port_oracle):
     # an imported image of a one-class index rebuilds the same layout (with several classes the image does not hold
     # the (group, low) order the layout is built on: such an index answers through the general path)
     c = random_case(42, n_t=50000, n_q=30000, n_groups=6, span=5_000_000, max_len=3000)
-    with env(BCU_BIN_ROWS=2048):
+    with env(BCU_BINNED=1, BCU_BIN_ROWS=2048):
         ix = DeviceIndex.build(c["tl"], c["th"], c["tg"])
     assert ix.info()["n_components"] == 1 and ix.info()["binned_tiles"] > 0
     with env(BCU_BINNED=1):
@@ -168,7 +169,7 @@ def test_binned_equals_general_path_on_the_same_index(port_oracle):
     image = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
     ix.export_dev(image.data_ptr(), nbytes, stream)
-    with env(BCU_BIN_ROWS=2048):
+    with env(BCU_BINNED=1, BCU_BIN_ROWS=2048):
         ix2 = DeviceIndex.import_dev(0, image.data_ptr(), nbytes, stream)
     assert ix2.info() == ix.info()
     with env(BCU_BINNED=1):

@@ -4,7 +4,7 @@ the UNMODIFIED reference tool (oracle/_ref/libsv2nl_ref.so, see tests/test_sv2nl
 line count and an order-independent hash of the lines of each of the three output files (the reference does not
 define the order: its tasks interleave).
 
-Default size 100 k SV x 500 k NL records so that the suite stays within minutes (the reference tool re-parses both
+Default size 60 k SV x 300 k NL records so that the suite stays within minutes (the reference tool re-parses both
 files in every chromosome task, mapper.hpp:196-197); BCU_TEST_FULL_E=1 runs the configuration's own 1 M x 5 M
 (profiles/r02_config_e.txt holds that run)."""
 import os
@@ -22,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_config_e_full_set_count_and_hash(tmp_path):
     full = bool(os.environ.get("BCU_TEST_FULL_E"))
-    n_sv, n_nl = (1_000_000, 5_000_000) if full else (100_000, 500_000)
+    n_sv, n_nl = (1_000_000, 5_000_000) if full else (60_000, 300_000)
     nl_path, sv_path = write_config_e_vcfs(str(tmp_path), n_sv, n_nl)
     tool_dir = os.path.join(ROOT, "standalone", "sv2nl")
     r = subprocess.run(["make", "-C", tool_dir, "sv2nl"], capture_output=True, text=True)

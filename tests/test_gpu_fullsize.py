@@ -4,7 +4,7 @@
   copy-in / run / copy-out streams, chained offset bases, segmented pair copies) with enough queries for
   several pipeline chunks, and once more with ``BCU_HOST_CHUNK=4096`` so that quarter/half/tail chunks and
   dozens of chunk boundaries are hit;
-* BASELINE.json configs C (full 10 M queries) and D (10 M targets, a 25 M-query slice of the 100 M batch) by
+* BASELINE.json configs C (full 10 M queries) and D (10 M targets, a 16 M-query slice of the 100 M batch) by
   total, per-query counts and the order-independent pair hash against the CPU flat-index twin (itself pinned
   to the reference tree walk in tests/test_oracle.py).
 
@@ -181,7 +181,7 @@ def test_config_c_full_size(port_oracle):
 
 def test_config_d_ten_million_targets(port_oracle):
     """BASELINE.json configs[3]: the 10 M-target index (larger than L2, several length classes) against a
-    25 M-query slice taken from the MIDDLE of the 100 M-query stream (query_id_base != 0)."""
+    16 M-query slice taken from the MIDDLE of the 100 M-query stream (query_id_base != 0)."""
     total, info = _device_join_count_hash(port_oracle, synth.CONFIG_D, synth.CONFIG_D.n_targets, 37_500_000,
-                                          25_000_000)
+                                          16_000_000)
     assert total > 10**8 and info["n_targets"] == 10_000_000
