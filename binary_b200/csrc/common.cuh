@@ -168,6 +168,16 @@ struct bcu_index {
   uint16_t* d_bn_cell2bin = nullptr;   // [bn_cells] (used while building the coverage lists)
   uint32_t* d_bn_cellbits = nullptr;   // [2 * ceil(bn_cells / 32)] routing table of the sort kernel: bit i = cell i is the
                                        // first cell of a bin, then the number of such bits before every word
+  // stab lists of the long-range emit (join.cu emit_long_kernel), only built for densely covered indexes:
+  // per segment and coordinate bin of width 2^lc_shift, the rows with low < bin start <= high ({high, id} columns)
+  // and the first row with low >= bin start. lc_bins == 0: none.
+  uint32_t lc_shift = 0;
+  uint64_t lc_bins = 0, lc_entries = 0;
+  uint2* d_lc_seg = nullptr;       // [n_comp][n_groups] {first bin slot, number of bins (0 = no lists)}
+  uint32_t* d_lc_off = nullptr;    // [lc_bins + 1] list of bin slot s = entries [off[s], off[s+1])
+  uint32_t* d_lc_row0 = nullptr;   // [lc_bins]
+  uint32_t* d_lc_high = nullptr;   // [lc_entries]
+  uint32_t* d_lc_id = nullptr;     // [lc_entries]
 };
 
 namespace bcu {
@@ -197,6 +207,8 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
 // (group, low)-sorted arrays ix->d_bn_*; group_cmax[g] = largest coordinate of the group
 int build_bin_layout(bcu_index* ix, const uint32_t* group_gval, const uint32_t* group_begin,
                      const uint32_t* group_cmax, cudaStream_t stream);
+// stab lists of a finished index (index_build.cu); a no-op unless the index is densely covered
+int build_long_lists(bcu_index* ix, cudaStream_t stream);
 // the binned join (binned_join.cu); returns BCU_NOT_TAKEN when the call is not eligible: the caller then runs
 // the general path
 constexpr int BCU_NOT_TAKEN = 1;

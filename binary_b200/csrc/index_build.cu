@@ -278,6 +278,11 @@ static void free_index_members(bcu_index* ix) {
   cudaFreeAsync(ix->d_bn_cell2bin, nullptr);
   cudaFreeAsync(ix->d_bn_cellbits, nullptr);
   cudaFreeAsync(ix->d_bn_blob, nullptr);
+  cudaFreeAsync(ix->d_lc_seg, nullptr);
+  cudaFreeAsync(ix->d_lc_off, nullptr);
+  cudaFreeAsync(ix->d_lc_row0, nullptr);
+  cudaFreeAsync(ix->d_lc_high, nullptr);
+  cudaFreeAsync(ix->d_lc_id, nullptr);
   cudaGetLastError();
 }
 
@@ -605,6 +610,216 @@ static int build_on_device(bcu_index* ix, uint64_t n, const uint32_t* d_group, c
     ix->bn_owns_rows = false;
   }
   mark("bin layout");
+  BCU_TRY(build_long_lists(ix, stream));
+  mark("stab lists");
+  return BCU_OK;
+}
+
+// ---- stab lists (join.cu emit_long_kernel) ---------------------------------------------------------------
+// A query whose candidate range [lb, ub) is long walks rows that start up to one maximal length before it; on
+// densely covered data with a broad length law about half of them do not reach the query. Per segment and
+// coordinate bin of width 2^lc_shift the index therefore keeps ONE contiguous block of {high, id} entries:
+//   * the stab list of the bin: the rows with low < bin start <= high -- every hit that starts before the bin is
+//     among them, and all but the few ending in the bin's first part are hits;
+//   * then the bin's own rows (bin start <= low < next bin start) in row order.
+// A query with q.low in the bin scans the block up to its exact upper bound (and, rarely, the rows of the following
+// bins from the plain columns): the candidates shrink from (max_len + q.len) / spacing rows to
+// coverage + (bin width / 2 + q.len) / spacing. Every segment has one extra, empty bin at its end so that
+// row0[s + 1] is the end of bin s's rows for every real bin.
+struct LcSeg { uint32_t row_begin, row_end, base, nb; };
+
+__global__ void __launch_bounds__(kThreads)
+    length_sum_kernel(const uint2* __restrict__ lowhigh, uint64_t n, unsigned long long* sum) {
+  unsigned long long acc = 0;
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
+    const uint2 v = lowhigh[r];
+    if (v.y > v.x) acc += v.y - v.x;
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(sum, acc);
+}
+
+// FILL = false: slots[s] counts the stab-list entries of bin slot s; FILL = true: slots[s] is the slot's write
+// cursor (starts at off[s]) and every row is also copied to its place among its own bin's rows, which end the block
+template <bool FILL>
+__global__ void __launch_bounds__(kThreads)
+    lc_rows_kernel(const LcSeg* __restrict__ segs, uint32_t n_segs, const uint2* __restrict__ lowhigh,
+                   const uint32_t* __restrict__ ids, uint64_t n, uint32_t shift, uint32_t* __restrict__ slots,
+                   const uint32_t* __restrict__ off, const uint32_t* __restrict__ row0,
+                   uint32_t* __restrict__ out_high, uint32_t* __restrict__ out_id) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const uint2 v = lowhigh[r];
+  if (!FILL && v.y <= v.x) return;  // low < start <= high needs a proper row of length >= 1
+  uint32_t lo = 0, hi = n_segs;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (segs[mid].row_begin <= r) lo = mid; else hi = mid;
+  }
+  const LcSeg s = segs[lo];
+  const uint32_t id = FILL ? ids[r] : 0u;
+  if (FILL) {
+    const uint32_t slot = s.base + min(v.x >> shift, s.nb - 2);  // (nb counts the empty end bin)
+    const uint32_t p = off[slot + 1] - (row0[slot + 1] - (uint32_t)r);
+    out_high[p] = v.y;
+    out_id[p] = id;
+    if (v.y <= v.x) return;
+  }
+  const uint32_t b0 = (v.x >> shift) + 1, b1 = min(v.y >> shift, s.nb - 2);
+  for (uint32_t b = b0; b <= b1 && b >= b0; ++b) {
+    const uint32_t p = atomicAdd(slots + s.base + b, 1u);
+    if (FILL) { out_high[p] = v.y; out_id[p] = id; }
+  }
+}
+
+// cnt[s] += rows of bin s (0 for the end bin of a segment)
+__global__ void __launch_bounds__(kThreads)
+    lc_block_size_kernel(const LcSeg* __restrict__ segs, uint32_t n_segs, const uint32_t* __restrict__ row0, uint64_t n_slots,
+                         uint32_t* __restrict__ cnt) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_slots) return;
+  uint32_t lo = 0, hi = n_segs;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (segs[mid].base <= i) lo = mid; else hi = mid;
+  }
+  if (i - segs[lo].base + 1 < segs[lo].nb) cnt[i] += row0[i + 1] - row0[i];
+}
+
+__global__ void __launch_bounds__(kThreads)
+    lc_row0_kernel(const LcSeg* __restrict__ segs, uint32_t n_segs, const uint2* __restrict__ lowhigh, uint32_t shift,
+                   uint64_t n_slots, uint32_t* __restrict__ row0) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_slots) return;
+  uint32_t lo = 0, hi = n_segs;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (segs[mid].base <= i) lo = mid; else hi = mid;
+  }
+  const LcSeg s = segs[lo];
+  const uint64_t x = (i - s.base) << shift;
+  uint32_t a = s.row_begin, e = s.row_end;
+  while (a < e) {
+    const uint32_t m = a + ((e - a) >> 1);
+    if ((uint64_t)lowhigh[m].x < x) a = m + 1; else e = m;
+  }
+  row0[i] = a;
+}
+
+// BCU_LONG_LISTS=0 never, =1 always (tests), default: when the summed target length is >= BCU_LONG_LISTS_COVER (16)
+// times the summed coordinate extent of the groups, i.e. when nearly every query's candidate range is long.
+int build_long_lists(bcu_index* ix, cudaStream_t stream) {
+  const char* e = std::getenv("BCU_LONG_LISTS");
+  const int mode = e ? std::atoi(e) : -1;
+  if (mode == 0 || ix->n == 0 || ix->n_groups == 0) return BCU_OK;
+  const uint64_t n = ix->n;
+  const uint32_t n_slots = ix->n_comp * ix->n_groups;
+  std::vector<GroupDesc> table(n_slots);
+  TempBuffers tmp(stream);
+  unsigned long long* d_sum;
+  BCU_CUDA(tmp.alloc(&d_sum, 1));
+  BCU_CUDA(cudaMemsetAsync(d_sum, 0, 8, stream));
+  length_sum_kernel<<<(unsigned)std::min<uint64_t>((n + kThreads - 1) / kThreads, 4096), kThreads, 0, stream>>>(ix->d_lowhigh, n, d_sum);
+  BCU_LAUNCHED();
+  unsigned long long sum_len = 0;
+  BCU_CUDA(cudaMemcpyAsync(&sum_len, d_sum, 8, cudaMemcpyDeviceToHost, stream));
+  BCU_CUDA(cudaMemcpyAsync(table.data(), ix->d_groups, table.size() * sizeof(GroupDesc), cudaMemcpyDeviceToHost, stream));
+  BCU_CUDA(cudaStreamSynchronize(stream));
+  // coordinate extent of each group as the directories bound it (an importer sees the same numbers)
+  uint64_t extent = 0;
+  for (uint32_t g = 0; g < ix->n_groups; ++g) {
+    uint64_t x = 0;
+    for (uint32_t c = 0; c < ix->n_comp; ++c) {
+      const GroupDesc& d = table[(size_t)c * ix->n_groups + g];
+      if (d.row_end > d.row_begin) x = std::max<uint64_t>(x, (uint64_t)d.nb << d.shift);
+    }
+    extent += x;
+  }
+  const char* ce = std::getenv("BCU_LONG_LISTS_COVER");
+  const double need = ce ? std::atof(ce) : 16.0;
+  if (mode != 1 && (double)sum_len < need * (double)extent) return BCU_OK;
+  // bin width: a quarter of the mean length (about 4 list entries per row), and no row in more than 4096 lists
+  const uint64_t mean_len = sum_len / n;
+  uint32_t shift = 4;
+  while (shift < 31 && ((1ull << shift) < mean_len / 4 || (1ull << shift) < (uint64_t)ix->max_len / 4096)) ++shift;
+  if ((sum_len >> shift) + 2 * n > 0x7fffffffull) return BCU_OK;  // entries must stay 32-bit
+  std::vector<LcSeg> segs;
+  std::vector<uint2> seg_table(n_slots, make_uint2(0u, 0u));
+  uint64_t n_bins = 0;
+  for (uint32_t i = 0; i < n_slots; ++i) {  // class-major = ascending rows
+    const GroupDesc& d = table[i];
+    if (d.row_end <= d.row_begin) continue;
+    const uint64_t cmax = ((uint64_t)d.nb << d.shift) - 1;
+    LcSeg s;
+    s.row_begin = d.row_begin; s.row_end = d.row_end;
+    s.nb = (uint32_t)((cmax >> shift) + 2);  // + the empty end bin
+    if (n_bins + s.nb > 0xffffffffull) return BCU_OK;
+    s.base = (uint32_t)n_bins;
+    seg_table[i] = make_uint2(s.base, s.nb);
+    n_bins += s.nb;
+    segs.push_back(s);
+  }
+  if (segs.empty() || (mode != 1 && n_bins > 4 * n + 4096ull * segs.size())) return BCU_OK;  // sparse extents
+  LcSeg* d_segs;
+  uint32_t* d_cnt;
+  BCU_CUDA(tmp.alloc(&d_segs, segs.size()));
+  BCU_CUDA(tmp.alloc(&d_cnt, n_bins + 1));
+  BCU_CUDA(cudaMemcpyAsync(d_segs, segs.data(), segs.size() * sizeof(LcSeg), cudaMemcpyHostToDevice, stream));
+  BCU_CUDA(cudaMemsetAsync(d_cnt, 0, (n_bins + 1) * 4, stream));
+  const unsigned row_grid = (unsigned)((n + kThreads - 1) / kThreads);
+  const unsigned slot_grid = (unsigned)((n_bins + kThreads - 1) / kThreads);
+  lc_rows_kernel<false><<<row_grid, kThreads, 0, stream>>>(d_segs, (uint32_t)segs.size(), ix->d_lowhigh, ix->d_id, n, shift,
+                                                            d_cnt, nullptr, nullptr, nullptr, nullptr);
+  BCU_LAUNCHED();
+  uint32_t *d_off = nullptr, *d_row0 = nullptr;
+  BCU_CUDA(cudaMallocAsync((void**)&d_off, (n_bins + 1) * 4, stream));
+  if (cudaMallocAsync((void**)&d_row0, (n_bins + 1) * 4, stream) != cudaSuccess) {
+    cudaFreeAsync(d_off, stream);
+    set_error("stab lists: out of device memory");
+    return BCU_E_NOMEM;
+  }
+  lc_row0_kernel<<<slot_grid, kThreads, 0, stream>>>(d_segs, (uint32_t)segs.size(), ix->d_lowhigh, shift, n_bins, d_row0);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  lc_block_size_kernel<<<slot_grid, kThreads, 0, stream>>>(d_segs, (uint32_t)segs.size(), d_row0, n_bins, d_cnt);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  int rc = exclusive_sum_u32(d_cnt, d_off, n_bins + 1, stream);
+  uint32_t entries = 0;
+  if (rc == BCU_OK && (cudaMemcpyAsync(&entries, d_off + n_bins, 4, cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+                       cudaStreamSynchronize(stream) != cudaSuccess)) rc = BCU_E_CUDA;
+  if (rc != BCU_OK || (mode != 1 && entries > 9 * n)) {  // (a few very long rows: the lists would outweigh the index)
+    cudaFreeAsync(d_off, stream);
+    cudaFreeAsync(d_row0, stream);
+    if (rc != BCU_OK) set_error("stab lists: %s", cudaGetErrorString(cudaGetLastError()));
+    return rc;
+  }
+  uint32_t *d_lh = nullptr, *d_li = nullptr;
+  uint2* d_seg_table = nullptr;
+  auto fail = [&](int code) {
+    cudaFreeAsync(d_off, stream); cudaFreeAsync(d_row0, stream); cudaFreeAsync(d_lh, stream);
+    cudaFreeAsync(d_li, stream); cudaFreeAsync(d_seg_table, stream);
+    set_error("stab lists: %s", code == BCU_E_NOMEM ? "out of device memory" : cudaGetErrorString(cudaGetLastError()));
+    return code;
+  };
+  if (cudaMallocAsync((void**)&d_lh, ((uint64_t)entries + 4) * 4, stream) != cudaSuccess ||
+      cudaMallocAsync((void**)&d_li, ((uint64_t)entries + 4) * 4, stream) != cudaSuccess ||
+      cudaMallocAsync((void**)&d_seg_table, n_slots * sizeof(uint2), stream) != cudaSuccess) return fail(BCU_E_NOMEM);
+  if (cudaMemcpyAsync(d_cnt, d_off, (n_bins + 1) * 4, cudaMemcpyDeviceToDevice, stream) != cudaSuccess ||
+      cudaMemcpyAsync(d_seg_table, seg_table.data(), n_slots * sizeof(uint2), cudaMemcpyHostToDevice, stream) != cudaSuccess)
+    return fail(BCU_E_CUDA);
+  lc_rows_kernel<true><<<row_grid, kThreads, 0, stream>>>(d_segs, (uint32_t)segs.size(), ix->d_lowhigh, ix->d_id, n, shift,
+                                                           d_cnt, d_off, d_row0, d_lh, d_li);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess) return fail(BCU_E_CUDA);  // host vectors
+  ix->lc_shift = shift;
+  ix->lc_bins = n_bins;
+  ix->lc_entries = entries;
+  ix->d_lc_seg = d_seg_table;
+  ix->d_lc_off = d_off;
+  ix->d_lc_row0 = d_row0;
+  ix->d_lc_high = d_lh;
+  ix->d_lc_id = d_li;
+  ix->bytes += (2 * n_bins + 2) * 4 + 2 * ((uint64_t)entries + 4) * 4 + n_slots * sizeof(uint2);
   return BCU_OK;
 }
 
@@ -1131,6 +1346,16 @@ extern "C" int bcu_index_import_dev(int device, const void* d_image, uint64_t by
       rc = build_bin_layout(ix, gval.data(), begin.data(), cmax.data(), stream);
     }
     ix->bytes = bytes_before;  // `bytes` travels in the header and already counts the exporter's layout
+    if (rc != BCU_OK) {
+      free_index_members(ix);
+      delete ix;
+      return rc;
+    }
+  }
+  if (ix->n) {  // derived data as well: the stab lists of the long-range emit
+    const uint64_t bytes_before = ix->bytes;
+    rc = build_long_lists(ix, stream);
+    ix->bytes = bytes_before;
     if (rc != BCU_OK) {
       free_index_members(ix);
       delete ix;

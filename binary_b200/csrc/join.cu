@@ -104,6 +104,14 @@ struct JoinArgs {
   uint32_t filter_diff;
   uint32_t filter_use_strand;
   const uint8_t* __restrict__ qstrand;  // INV: per query, bit0 = strand1 is '+', bit1 = strand2 is '+'
+  // stab lists (index_build.cu build_long_lists), lc_seg == nullptr: none
+  const uint2* __restrict__ lc_seg;
+  const uint32_t* __restrict__ lc_off;
+  const uint32_t* __restrict__ lc_row0;
+  const uint32_t* __restrict__ lc_high;
+  const uint32_t* __restrict__ lc_id;
+  uint32_t lc_shift;
+  uint64_t lc_entries, lc_bins;
 };
 
 struct GroupTables {
@@ -964,6 +972,7 @@ __global__ void __launch_bounds__(kJoinThreads, kLongMinBlocks) emit_long_kernel
     LongRange mine;
     mine.lb = mine.ub = mine.ql = mine.qh = mine.strand = mine.cnt = mine.qid = 0;
     mine.base = 0;
+    uint32_t cov_b = 0, cov_e = 0;  // the block of the bin holding q.low, when the index has stab lists
     if (have) {
       const uint32_t v = list[i0 + lane], q = v >> a.comp_shift;
       mine.lb = a.st_lb[v];
@@ -977,6 +986,25 @@ __global__ void __launch_bounds__(kJoinThreads, kLongMinBlocks) emit_long_kernel
         pos += (w & kBigFlag) ? (w & ~kBigFlag) : (uint32_t)__popc(w);
       }
       mine.base = pos;
+      if (a.lc_seg && mine.cnt != 0 && mine.ql <= a.qhigh[q]) {  // (an inverted query keeps the plain scan)
+        const uint32_t qg = a.qgroup ? a.qgroup[q] : 0u;
+        uint32_t lo = 0, hi = a.n_groups;
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (a.groups[mid].gval < qg) lo = mid + 1; else hi = mid;
+        }
+        const uint2 seg = lo < a.n_groups ? a.lc_seg[(v & (a.n_comp - 1u)) * a.n_groups + lo] : make_uint2(0u, 0u);
+        const uint32_t b = mine.ql >> a.lc_shift;
+        if (b + 1 < seg.y) {  // (seg.y counts the empty end bin)
+          BCU_DEV_ASSERT((uint64_t)seg.x + b + 1 < a.lc_bins);
+          // the bin's block = stab list (the hits that start before the bin) + the bin's own rows; the rows of the
+          // following bins up to ub, if any, come from the plain columns
+          const uint32_t r1 = a.lc_row0[seg.x + b + 1];
+          cov_b = a.lc_off[seg.x + b];
+          cov_e = a.lc_off[seg.x + b + 1] - (r1 > mine.ub ? r1 - mine.ub : 0u);
+          mine.lb = max(mine.lb, r1);
+        }
+      }
     }
     unsigned todo = __ballot_sync(0xffffffffu, have && mine.cnt != 0);
     while (todo) {
@@ -990,16 +1018,32 @@ __global__ void __launch_bounds__(kJoinThreads, kLongMinBlocks) emit_long_kernel
       R.qid = __shfl_sync(0xffffffffu, mine.qid, src);
       R.base = shfl_u64(mine.base, src);
       R.qh = R.strand = 0;
+      const uint32_t cb = __shfl_sync(0xffffffffu, cov_b, src), ce = __shfl_sync(0xffffffffu, cov_e, src);
       uint32_t* out = c.hit_target + R.base;
       const uint32_t lim = c.capacity > R.base ? (uint32_t)min(c.capacity - R.base, (uint64_t)0xffffffffu) : 0u;
       // (measured and not kept: a predicate-free path for whole 128-row blocks, writing the query id next
       // to each hit instead of the fill below, and 4 rows per lane with 128-bit loads)
       uint32_t count = 0;
-      for (uint32_t r0 = R.lb; r0 < R.ub; r0 += 32 * kTrips) {
+      if (ce > cb) {
+        LongCtx c2 = c;
+        c2.high = a.lc_high;
+        c2.ids = a.lc_id;
+        c2.n_rows = a.lc_entries;
+        LongRange R2 = R;
+        R2.lb = cb;
+        R2.ub = ce;
+        for (uint32_t r0 = cb; r0 < ce; r0 += 32 * kTrips) {
+          LongRegs g;
+          long_preload<true, false>(c2, lane, R2, r0, g);
+          long_consume<true, false>(c2, lane, R2, r0, g, out, lim, count);
+        }
+      }
+      for (uint32_t r0 = R.lb; r0 < R.ub; r0 += 32 * kTrips) {  // (with a block: only when the query leaves its bin)
         LongRegs g;
         long_preload<true, false>(c, lane, R, r0, g);
         long_consume<true, false>(c, lane, R, r0, g, out, lim, count);
       }
+      BCU_DEV_ASSERT(count == R.cnt);
       if (c.hit_query) {  // the query-id column of a range is one value: coalesced fill
         uint32_t* qcol = c.hit_query + R.base;
         const uint32_t n = min(R.cnt, lim);
@@ -1189,6 +1233,14 @@ int launch_join(const bcu_index* ix, int mode, uint64_t n_q, const uint32_t* d_q
   a.filter_diff = filt ? filter->diff : 0u;
   a.filter_use_strand = filt ? filter->use_strand : 0u;
   a.qstrand = filt ? d_qstrand : nullptr;
+  a.lc_seg = ix->lc_bins ? ix->d_lc_seg : nullptr;
+  a.lc_off = ix->d_lc_off;
+  a.lc_row0 = ix->d_lc_row0;
+  a.lc_high = ix->d_lc_high;
+  a.lc_id = ix->d_lc_id;
+  a.lc_shift = ix->lc_shift;
+  a.lc_entries = ix->lc_entries;
+  a.lc_bins = ix->lc_bins;
   if (filt && !prefix) { set_error("pair filters are only supported by the count/join entry points"); return BCU_E_INVALID; }
   if (filt && filter->kind != BCU_FILTER_SV2NL_DUP && filter->kind != BCU_FILTER_SV2NL_INV) {
     set_error("unknown pair filter kind %u", filter->kind);

@@ -1,4 +1,7 @@
 """Shared input builders for the parity tests (seeded; no reference files are read at run time)."""
+import os
+from contextlib import contextmanager
+
 import numpy as np
 
 # The reference's own fixture: test/source/test_algorithm/test_interval_tree.cpp:88-92,112-116
@@ -188,3 +191,17 @@ def line_set_digest(lines):
     for l in lines:
         h = (h + int.from_bytes(hashlib.blake2b(l.encode(), digest_size=8).digest(), "little")) & 0xFFFFFFFFFFFFFFFF
     return len(lines), h
+
+
+@contextmanager
+def env(**kw):
+    old = {k: os.environ.get(k) for k in kw}
+    os.environ.update({k: str(v) for k, v in kw.items()})
+    try:
+        yield
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v

@@ -7,29 +7,14 @@ size: tests/test_gpu_fullsize.py); here ``BCU_BINNED=1`` forces it on oracle-siz
 shrinks the tiles so that small indexes still have many bins, halos and queries reaching past their bin.
 """
 import os
-from contextlib import contextmanager
 
 import numpy as np
 import pytest
 
 from binary_b200 import DeviceIndex, synth
-from cases import canonical, random_case
+from cases import canonical, env, random_case
 
 pytestmark = pytest.mark.gpu
-
-
-@contextmanager
-def env(**kw):
-    old = {k: os.environ.get(k) for k in kw}
-    os.environ.update({k: str(v) for k, v in kw.items()})
-    try:
-        yield
-    finally:
-        for k, v in old.items():
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v
 
 
 def dev_join(ix, ql, qh, qg, qid_base=0, cap=None, count_only=False):

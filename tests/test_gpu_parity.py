@@ -423,6 +423,53 @@ def test_long_ranges_rank_count_and_its_fallbacks(port_oracle, label):
     assert hits > 30 * c["ql"].size or label in ("inverted_queries", "length_classes", "point_targets")
 
 
+@pytest.mark.parametrize("label", ["proper", "inverted_rows_and_queries", "length_classes", "groups_unknown_to_index"])
+def test_stab_lists_of_the_long_range_emit(port_oracle, label):
+    """emit_long_kernel with the stab lists (index_build.cu build_long_lists: rows with low < bin start <= high, per
+    coordinate bin) against the plain range scan on the same data and against the oracle; inverted queries keep
+    the scan, inverted rows are never listed, an imported image rebuilds the lists."""
+    import torch
+    from cases import env
+    from test_gpu_binned import dev_join
+    rng = np.random.default_rng(99)
+    kw = dict(n_t=30000, n_q=5000, span=400000, max_len=70000, n_groups=3, dup_frac=0.02)
+    if label == "length_classes":
+        kw.update(span=4_000_000, max_len=30000, long_frac=0.02)
+    if label == "groups_unknown_to_index":
+        kw.update(q_groups=5)
+    c = random_case(55, **kw)
+    if label == "inverted_rows_and_queries":
+        idx = rng.choice(c["tl"].size, c["tl"].size // 25, replace=False)
+        c["th"][idx] = c["tl"][idx] // 2
+        idx = rng.choice(c["ql"].size, c["ql"].size // 6, replace=False)
+        c["ql"][idx], c["qh"][idx] = c["qh"][idx].copy(), c["ql"][idx].copy()
+    f = port_oracle.build(c["tl"], c["th"], c["tg"])
+    want_off, want_tid = f.query_sorted_pairs(c["ql"], c["qh"], c["qg"], threads=4)
+    sizes = {}
+    for lists in (0, 1):
+        with env(BCU_LONG_LISTS=lists, BCU_BINNED=0):
+            ix = DeviceIndex.build(c["tl"], c["th"], c["tg"])
+            sizes[lists] = ix.info()["device_bytes"]
+            off, hq, ht = dev_join(ix, c["ql"], c["qh"], c["qg"], qid_base=7)
+            assert np.array_equal(off, want_off) and np.array_equal(canonical(off, ht)[1], want_tid)
+            off_h, hq_h, ht_h = ix.join(c["ql"], c["qh"], c["qg"])                     # host-buffer pipeline
+            assert np.array_equal(off_h, want_off) and np.array_equal(canonical(off_h, ht_h)[1], want_tid)
+            if lists:
+                dev = torch.device("cuda:0")
+                nbytes = ix.image_size()
+                image = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+                stream = torch.cuda.current_stream().cuda_stream
+                ix.export_dev(image.data_ptr(), nbytes, stream)
+                ix2 = DeviceIndex.import_dev(0, image.data_ptr(), nbytes, stream)
+                assert ix2.info()["device_bytes"] == sizes[1]
+                off2, _, ht2 = dev_join(ix2, c["ql"], c["qh"], c["qg"])
+                assert np.array_equal(off2, want_off) and np.array_equal(canonical(off2, ht2)[1], want_tid)
+                ix2.close()
+            ix.close()
+    assert sizes[1] > sizes[0]                       # the lists were built when asked for, and only then
+    assert int(want_off[-1]) > 20 * c["ql"].size or label == "length_classes"
+
+
 @pytest.mark.parametrize("cap", [0, 1, 37, 5000])
 def test_pair_capacity_never_writes_past_the_buffer(port_oracle, cap):
     """bcu_join_dev with a pair buffer smaller than the result: offsets and total are complete, positions
