@@ -33,6 +33,13 @@ class Filter(C.Structure):
 FILTER_NONE, FILTER_SV2NL_DUP, FILTER_SV2NL_INV = 0, 1, 2
 
 
+class Sv2nlRules(C.Structure):
+    """``bcu_sv2nl_rules``: what follows the join inside one sv2nl mapper (TRA condition, duplicate-key rule)."""
+    _fields_ = [("probes_per_record", C.c_uint32), ("tra", C.c_uint32), ("diff", C.c_uint32), ("dedup", C.c_uint32),
+                ("rec_p1", vp), ("rec_p2", vp), ("tgt_p1", vp), ("tgt_p2", vp), ("tgt_pos", vp), ("tgt_end", vp),
+                ("rec_key", vp)]
+
+
 class IndexInfo(C.Structure):
     _fields_ = [("n_targets", C.c_uint64), ("n_groups", C.c_uint32), ("n_components", C.c_uint32),
                 ("bin_shift", C.c_uint32), ("sort_passes", C.c_uint32), ("n_bins", C.c_uint64),
@@ -66,6 +73,7 @@ SIGNATURES = {
     "bcu_index_image_size": (C.c_int, [vp, C.POINTER(C.c_uint64)]),
     "bcu_index_export_dev": (C.c_int, [vp, vp, C.c_uint64, vp]),
     "bcu_index_import_dev": (C.c_int, [C.c_int, vp, C.c_uint64, vp, C.POINTER(vp)]),
+    "bcu_sv2nl_join": (C.c_int, [vp, vp, vp, C.c_uint64, vp, vp, vp, vp, vp, C.c_uint64, vp, u64p]),
     "bcu_launch_count": (C.c_uint64, []),
 }
 

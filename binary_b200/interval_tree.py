@@ -178,6 +178,51 @@ class DeviceIndex:
             return offsets, hq[: total.value], ht[: total.value]
         raise _lib.BinaryCudaError(_lib.BCU_E_CAPACITY, "pair capacity still too small after growing")
 
+    def sv2nl_join(self, qlow, qhigh, qgroup=None, *, kind: int = _lib.FILTER_NONE, diff: int = 1_000_000,
+                   use_strand: bool = True, qstrand=None, probes_per_record: int = 1, tra=None, rec_key=None,
+                   pair_capacity: Optional[int] = None):
+        """``bcu_sv2nl_join``: one sv2nl mapper on the device -- the (filtered) join, then TraMapper's
+        ``check_condition`` (``tra`` = dict of the six breakpoint columns rec_p1, rec_p2, tgt_p1, tgt_p2, tgt_pos,
+        tgt_end) and the duplicate-key rule (``rec_key``: [n_rec, 4] u32). Returns per-RECORD (offsets, targets)."""
+        qlow, qhigh, qgroup = self._queries(qlow, qhigh, qgroup)
+        if qlow.size % probes_per_record:
+            raise ValueError("the number of queries is not a multiple of probes_per_record")
+        n_rec = qlow.size // probes_per_record
+        qs = None if qstrand is None else np.ascontiguousarray(qstrand, dtype=np.uint8)
+        u32 = lambda a: np.ascontiguousarray(a, dtype=np.uint32)
+        keep = []  # the structure holds raw pointers: keep the arrays alive
+        rules = _lib.Sv2nlRules(probes_per_record, int(tra is not None), diff, int(rec_key is not None),
+                                None, None, None, None, None, None, None)
+        if tra is not None:
+            for name in ("rec_p1", "rec_p2", "tgt_p1", "tgt_p2", "tgt_pos", "tgt_end"):
+                arr = u32(tra[name])
+                if arr.size != (n_rec if name.startswith("rec") else len(self)):
+                    raise ValueError(f"{name}: wrong length")
+                keep.append(arr)
+                setattr(rules, name, arr.ctypes.data)
+        if rec_key is not None:
+            key = u32(rec_key).reshape(-1)
+            if key.size != 4 * n_rec:
+                raise ValueError("rec_key must hold four words per record")
+            keep.append(key)
+            rules.rec_key = key.ctypes.data
+        flt = _lib.Filter(kind, diff, int(bool(use_strand)), 0)
+        offsets = np.empty(n_rec + 1, dtype=np.uint64)
+        cap = int(pair_capacity) if pair_capacity is not None else max(2 * qlow.size, 1 << 16)
+        total = C.c_uint64()
+        lib = _lib.load()
+        for _ in range(2):
+            ht = np.empty(cap, dtype=np.uint32)
+            rc = lib.bcu_sv2nl_join(self._h, C.byref(flt) if kind != _lib.FILTER_NONE else None, C.byref(rules), n_rec,
+                                    _p(qgroup), _p(qlow), _p(qhigh), _p(qs), offsets.ctypes.data, cap, ht.ctypes.data,
+                                    C.byref(total))
+            if rc == _lib.BCU_E_CAPACITY:
+                cap = total.value
+                continue
+            check(rc)
+            return offsets, ht[: total.value]
+        raise _lib.BinaryCudaError(_lib.BCU_E_CAPACITY, "pair capacity still too small after growing")
+
     def any(self, qlow, qhigh, qgroup=None) -> np.ndarray:
         qlow, qhigh, qgroup = self._queries(qlow, qhigh, qgroup)
         out = np.empty(qlow.size, dtype=np.uint8)

@@ -5,9 +5,10 @@ Reference being restructured (``/root/reference/standalone/sv2nl``): ``Mapper::m
 record; ``TraMapper`` (``source/mapper.cpp:86-170``) shares one tree over all BND records. Here each of the
 three mappers issues ONE batched join for all chromosomes (chromosome = ``group``; Tra joins on the
 selective breakpoint-proximity condition instead of the raw interval, see below),
-with the DUP / INV post-filters (``check_condition``, ``mapper.cpp:50-79``) fused into the join kernels
-(``bcu_join_filtered``) and the TRA conditions (``mapper.cpp:144-156``) vectorised on the host, then the duplicate-key rule of ``SV2NL_USE_CACHE``
-(``mapper.hpp:212-234``) and the writer's formatting (``writer.cpp:21-27``).
+through ``bcu_sv2nl_join``: the DUP / INV post-filters (``check_condition``, ``mapper.cpp:50-79``) are fused into
+the join kernels, the TRA conditions (``mapper.cpp:144-156``) and the duplicate-key rule of ``SV2NL_USE_CACHE``
+(``mapper.hpp:212-234``) run on the device on the join's CSR (``csrc/sv2nl_rules.cu``); the host only formats the
+surviving lines (``writer.cpp:21-27``).
 
 Both VCFs are parsed once (``vcf_text.read_vcf``) instead of once per chromosome task. Output lines are
 the same multiset as the reference's; their order is not defined there (thread interleaving).
@@ -45,25 +46,10 @@ def _validated(t: VcfTable, sel: np.ndarray, swap_chroms: bool):
     return chrom, pos, end, chr2
 
 
-def _absdiff(a: np.ndarray, b: np.ndarray) -> np.ndarray:
-    a, b = a.astype(np.int64), b.astype(np.int64)
-    return np.abs(a - b)
-
-
 def _fmt(chrom, pos, end, svtype, chr2=None) -> str:  # writer.cpp:21-27, note pos + 1
     if chr2 is not None:
         return f"{chrom},{chr2}\t{int(pos) + 1}\t{int(end)}\t{svtype}"
     return f"{chrom}\t{int(pos) + 1}\t{int(end)}\t{svtype}"
-
-
-def _first_per_key_with_hits(keys: List[str], has_hits: np.ndarray) -> np.ndarray:
-    """SV2NL_USE_CACHE: an NL record is written only if no EARLIER record with the same key was written."""
-    seen, keep = set(), np.zeros(len(keys), dtype=bool)
-    for i, k in enumerate(keys):
-        if has_hits[i] and k not in seen:
-            seen.add(k)
-            keep[i] = True
-    return keep
 
 
 def map_sv2nl(nl: VcfTable, sv: VcfTable, diff: int = 1_000_000, use_strand: bool = True, device: int = 0
@@ -82,37 +68,20 @@ def map_sv2nl(nl: VcfTable, sv: VcfTable, diff: int = 1_000_000, use_strand: boo
             t_chrom, t_pos, t_end, _ = _validated(sv, tsel, swap_chroms=False)  # build_tree validates
             q_chrom, q_pos, q_end, _ = _validated(nl, qsel, swap_chroms=False)
             ix = DeviceIndex.build(t_pos, t_end, cid(t_chrom), device=device)
-            # check_condition is fused into the join kernels (bcu_join_filtered): rejected pairs are never
-            # counted or written. The host re-evaluation below is then a no-op kept as a cross-check.
+            # check_condition is fused into the join kernels and the duplicate-key rule runs on the join's CSR on the
+            # device: what comes back are the pairs that are written
             qstrand = (nl.strand1[qsel].astype(np.uint8) | (nl.strand2[qsel].astype(np.uint8) << 1))
-            off, hq, ht = ix.join_filtered(q_pos, q_end, cid(q_chrom),
-                                           kind=_lib.FILTER_SV2NL_DUP if name == "dup" else _lib.FILTER_SV2NL_INV,
-                                           diff=diff, use_strand=use_strand, qstrand=qstrand)
+            key = np.stack([cid(nl.chrom[qsel]), np.full(qsel.size, 0xFFFFFFFF, np.uint32),     # helper.hpp:84-91:
+                            nl.pos[qsel].astype(np.uint32), nl.svend[qsel].astype(np.uint32)], axis=1)  # ORIGINAL record
+            off, ht = ix.sv2nl_join(q_pos, q_end, cid(q_chrom),
+                                    kind=_lib.FILTER_SV2NL_DUP if name == "dup" else _lib.FILTER_SV2NL_INV,
+                                    diff=diff, use_strand=use_strand, qstrand=qstrand, rec_key=key)
             ix.close()
-            n_device = hq.size
-            nlp, nle, svp, sve = q_pos[hq], q_end[hq], t_pos[ht], t_end[ht]
-            sv_has_nl = (svp <= nlp) & (sve >= nle)                   # is_contained(sv, nl)
-            near = (_absdiff(nlp, svp) <= diff) & (_absdiff(nle, sve) <= diff)  # distance_less
-            if name == "dup":
-                ok = sv_has_nl & near
-            else:
-                nl_has_sv = (nlp <= svp) & (nle >= sve)
-                ok = ~sv_has_nl & ~nl_has_sv & near
-                if use_strand:
-                    s1, s2 = nl.strand1[qsel][hq], nl.strand2[qsel][hq]
-                    left = nlp <= svp
-                    ok &= np.where(left, s1 & ~s2, ~s1 & s2)
-            hq, ht = hq[ok], ht[ok]
-            if hq.size != n_device:
-                raise AssertionError("device filter and host check_condition disagree")
-            kept = np.bincount(hq, minlength=qsel.size) > 0
-            keys = [f"{nl.chrom[i]}-{int(nl.pos[i])}-{int(nl.svend[i])}" for i in qsel]  # helper.hpp:84-91
-            write = _first_per_key_with_hits(keys, kept)
-            for q, t in zip(hq, ht):
-                if write[q]:
-                    i, k = qsel[q], tsel[t]
-                    lines.append(_fmt(nl.chrom[i], nl.pos[i], nl.svend[i], nl.svtype[i]) + "\t" +
-                                 _fmt(t_chrom[t], t_pos[t], t_end[t], sv.svtype[k]))
+            for q in np.flatnonzero(np.diff(off)):
+                i = qsel[q]
+                left = _fmt(nl.chrom[i], nl.pos[i], nl.svend[i], nl.svtype[i])
+                for t in ht[int(off[q]):int(off[q + 1])]:
+                    lines.append(left + "\t" + _fmt(t_chrom[t], t_pos[t], t_end[t], sv.svtype[tsel[t]]))
         out[name] = lines
 
     # TraMapper. The reference joins on the raw [pos, POS2] intervals of ALL BND records (one tree, not
@@ -122,7 +91,7 @@ def map_sv2nl(nl: VcfTable, sv: VcfTable, diff: int = 1_000_000, use_strand: boo
     # Same result, far fewer pairs: join on the SELECTIVE condition -- group = ordered chromosome pair,
     # target = the point p1, query = [p1 - diff, p1 + diff] -- and apply the remaining conditions (second
     # breakpoint within diff, and the reference's raw-interval overlap, which can still reject a pair) on
-    # the host.
+    # the device as well (bcu_sv2nl_rules.tra).
     tsel = np.flatnonzero(sv.svtype == "BND")
     qsel = np.flatnonzero((nl.svtype == "TRA") & main)
     lines = []
@@ -144,23 +113,21 @@ def map_sv2nl(nl: VcfTable, sv: VcfTable, diff: int = 1_000_000, use_strand: boo
         q_hi = np.clip(p1 + diff, 0, 0xFFFFFFFF).astype(np.uint32)
         sp1u = sp1.astype(np.uint32)
         ix = DeviceIndex.build(sp1u, sp1u, t_group, device=device)
-        off, hq, ht = ix.join(q_lo, q_hi, q_group)
+        # format_map_key of the ORIGINAL record (helper.hpp:84-91): ordered chromosome pair + positions
+        o_c, o_c2 = nl.chrom[qsel], nl.chr2[qsel]
+        o_p, o_e = nl.pos[qsel].astype(np.uint32), nl.svend[qsel].astype(np.uint32)
+        sw = o_c > o_c2
+        key = np.stack([np.where(sw, cid(o_c2), cid(o_c)), np.where(sw, cid(o_c), cid(o_c2)),
+                        np.where(sw, o_e, o_p), np.where(sw, o_p, o_e)], axis=1)
+        tra = dict(rec_p1=np1, rec_p2=np2, tgt_p1=sp1, tgt_p2=sp2, tgt_pos=sv.pos[tsel], tgt_end=sv.svend[tsel])
+        off, ht = ix.sv2nl_join(q_lo, q_hi, q_group, diff=diff, tra=tra, rec_key=key)
         ix.close()
-        t_pos, t_end = sv.pos[tsel], sv.svend[tsel]
-        ok = (_absdiff(np1[hq], sp1[ht]) <= diff) & (_absdiff(np2[hq], sp2[ht]) <= diff)
-        ok &= (q_pos[hq] <= t_end[ht]) & (t_pos[ht] <= q_end[hq])   # the reference's raw overlap, as written
-        hq, ht = hq[ok], ht[ok]
-        kept = np.bincount(hq, minlength=qsel.size) > 0
-        keys = []
-        for i in qsel:  # format_map_key of the ORIGINAL record
-            c, c2, p, e = nl.chrom[i], nl.chr2[i], int(nl.pos[i]), int(nl.svend[i])
-            keys.append(f"{c2}-{c}-{e}-{p}" if c > c2 else f"{c}-{c2}-{p}-{e}")
-        write = _first_per_key_with_hits(keys, kept)
-        for q, t in zip(hq, ht):
-            if write[q]:
-                i, k = qsel[q], tsel[t]
-                lines.append(_fmt(nl.chrom[i], nl.pos[i], nl.svend[i], nl.svtype[i], nl.chr2[i]) + "\t" +
-                             _fmt(sv.chrom[k], sv.pos[k], sv.svend[k], sv.svtype[k], sv.chr2[k]))
+        for q in np.flatnonzero(np.diff(off)):
+            i = qsel[q]
+            left = _fmt(nl.chrom[i], nl.pos[i], nl.svend[i], nl.svtype[i], nl.chr2[i])
+            for t in ht[int(off[q]):int(off[q + 1])]:
+                k = tsel[t]
+                lines.append(left + "\t" + _fmt(sv.chrom[k], sv.pos[k], sv.svend[k], sv.svtype[k], sv.chr2[k]))
     out["tra"] = lines
     return out
 

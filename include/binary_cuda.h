@@ -186,6 +186,37 @@ int bcu_index_export_dev(const bcu_index* index, void* d_image, uint64_t bytes, 
 /* d_image: an exported image resident on `device`; the new index owns copies, d_image may be freed after. */
 int bcu_index_import_dev(int device, const void* d_image, uint64_t bytes, void* stream, bcu_index** out);
 
+/* ---- sv2nl: one mapper from its queries to the lines that are written ------
+ * The reference, per NL record of a mapper (standalone/sv2nl): find_overlaps -> filter(check_condition) ->
+ * SV2NL_USE_CACHE duplicate-key rule -> writer (include/mapper.hpp:194-236, source/mapper.cpp:86-126). This
+ * entry runs the (optionally filtered) join AND those rules on the device; only the final CSR returns:
+ *   - `filter` (may be NULL): DupMapper / InvMapper check_condition, fused into the join kernels (bcu_filter);
+ *   - rules->tra: TraMapper::check_condition (source/mapper.cpp:144-156) for the RE-KEYED translocation join --
+ *     group = ordered chromosome pair (x bucket of the second breakpoint), target = the point p1, query =
+ *     [p1 - diff, p1 + diff]; record r owns the `probes_per_record` consecutive queries r*p .. r*p + p - 1 (one
+ *     per bucket a partner's p2 can fall into). Kept are the pairs with |p1 - p1'| <= diff, |p2 - p2'| <= diff
+ *     whose raw intervals overlap as in the reference's tree of unvalidated BND records (mapper.cpp:103,158-170);
+ *   - rules->dedup: of the records with the same key (format_map_key, include/helper.hpp:84-91, as four words)
+ *     only the FIRST one with at least one kept pair keeps its pairs (include/mapper.hpp:204-229).
+ * offsets: n_rec + 1 entries, per RECORD. BCU_E_CAPACITY (offsets and *total complete, no pairs) if the kept
+ * pairs exceed pair_capacity. All pointers are host pointers; tgt_* are indexed by target id (insertion order). */
+typedef struct bcu_sv2nl_rules {
+  uint32_t probes_per_record; /* >= 1 */
+  uint32_t tra;               /* != 0: apply the TRA rule */
+  uint32_t diff;              /* sv2nl --dis */
+  uint32_t dedup;             /* != 0: apply the duplicate-key rule */
+  const uint32_t* rec_p1;     /* tra: [n_rec] ordered breakpoints (get_2chroms_with_pos, helper.hpp:76-82) */
+  const uint32_t* rec_p2;     /*      of the VALIDATED NL record */
+  const uint32_t* tgt_p1;     /* tra: [n_t] ordered breakpoints of the SV record (not validated) */
+  const uint32_t* tgt_p2;
+  const uint32_t* tgt_pos;    /* tra: [n_t] its POS / END as read: the interval the reference inserts */
+  const uint32_t* tgt_end;
+  const uint32_t* rec_key;    /* dedup: [4 * n_rec] */
+} bcu_sv2nl_rules;
+int bcu_sv2nl_join(const bcu_index* index, const bcu_filter* filter, const bcu_sv2nl_rules* rules, uint64_t n_rec,
+                   const uint32_t* qgroup, const uint32_t* qlow, const uint32_t* qhigh, const uint8_t* qstrand,
+                   uint64_t* offsets, uint64_t pair_capacity, uint32_t* hit_target, uint64_t* total);
+
 /* Number of kernel launches this library has issued on the calling process (all threads). */
 uint64_t bcu_launch_count(void);
 

@@ -5,12 +5,14 @@
 //                                                  chromosome, one find_overlaps per NL record)
 //   Dup/Inv/TraMapper::check_condition             source/mapper.cpp:50-79, 144-156
 //   TraMapper: one tree over all BND records       source/mapper.cpp:86-170
-//   validate_record, is_contained, distance_less,
-//   get_2chroms_with_pos, format_map_key           include/helper.hpp:16-91
+//   validate_record, get_2chroms_with_pos,
+//   format_map_key                                 include/helper.hpp:52-91
+//   is_contained, distance_less                    include/helper.hpp:16-41 (on the device: csrc/join.cu accept<>)
 //   SV2NL_USE_CACHE duplicate-key rule             include/mapper.hpp:212-234, options.hpp:8
-// Here every mapper issues ONE batched join over all chromosomes (chromosome = group), then runs the
-// reference's post-filters over the returned (query, target) pairs in query order. Both VCFs are parsed
-// once. Output lines equal the reference's as a multiset (its line order is thread-dependent).
+// Here every mapper issues ONE call, bcu_sv2nl_join, over all chromosomes (chromosome = group): the join, the
+// reference's post-filters and its duplicate-key rule run on the device (csrc/join.cu accept<>, csrc/sv2nl_rules.cu);
+// the host formats the pairs that come back. Both VCFs are parsed once. Output lines equal the reference's as a
+// multiset (its line order is thread-dependent).
 #pragma once
 
 #include <binary_cuda.h>
@@ -24,7 +26,6 @@
 #include <map>
 #include <string>
 #include <unordered_map>
-#include <unordered_set>
 #include <utility>
 #include <vector>
 
@@ -99,13 +100,6 @@ inline Rec validate_record(Rec r) {  // helper.hpp:52-63
   }
   return r;
 }
-inline bool is_contained(const Rec& target, const Rec& source) {  // helper.hpp:16-25
-  return target.pos <= source.pos && target.svend >= source.svend;
-}
-inline std::uint32_t absdiff(std::uint32_t a, std::uint32_t b) { return a >= b ? a - b : b - a; }
-inline bool distance_less(const Rec& a, const Rec& b, std::uint32_t thr) {  // helper.hpp:32-41
-  return absdiff(a.pos, b.pos) <= thr && absdiff(a.svend, b.svend) <= thr;
-}
 struct Breakpoints { std::uint32_t c1, c2, p1, p2; };
 inline Breakpoints ordered_breakpoints(const Rec& r) {  // get_2chroms_with_pos, helper.hpp:76-82
   return r.chrom > r.chr2 ? Breakpoints{r.chr2, r.chrom, r.svend, r.pos} : Breakpoints{r.chrom, r.chr2, r.pos, r.svend};
@@ -115,13 +109,6 @@ inline Breakpoints ordered_breakpoints(const Rec& r) {  // get_2chroms_with_pos,
 struct MapKey {
   std::uint32_t a, b, c, d;
   bool operator==(const MapKey& o) const { return a == o.a && b == o.b && c == o.c && d == o.d; }
-};
-struct MapKeyHash {
-  std::size_t operator()(const MapKey& k) const {
-    std::uint64_t x = ((std::uint64_t)k.a << 32 | k.b) * 0x9E3779B97F4A7C15ull ^ ((std::uint64_t)k.c << 32 | k.d);
-    x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
-    return (std::size_t)x;
-  }
 };
 inline MapKey map_key(const Rec& r) {
   if (r.two_chrom) {
@@ -148,28 +135,27 @@ struct JoinResult {
   std::vector<std::uint32_t> targets;
 };
 
-// one batched join through the C ABI; throws binary::VcfReaderError with the library's message on failure
-// filter == nullptr: plain overlap join; else sv2nl's DUP / INV check_condition runs inside the kernels
+// one mapper through the C ABI (join + post-filter + duplicate-key rule on the device); throws
+// binary::VcfReaderError with the library's message on failure. Returns the per-RECORD CSR of the written pairs.
 inline JoinResult gpu_join(int device, const std::vector<std::uint32_t>& tg, const std::vector<std::uint32_t>& tl,
                            const std::vector<std::uint32_t>& th, const std::vector<std::uint32_t>& qg,
                            const std::vector<std::uint32_t>& ql, const std::vector<std::uint32_t>& qh,
-                           const bcu_filter* filter = nullptr, const std::vector<std::uint8_t>* qstrand = nullptr) {
+                           const bcu_sv2nl_rules& rules, const bcu_filter* filter = nullptr,
+                           const std::vector<std::uint8_t>* qstrand = nullptr) {
   JoinResult r;
-  r.offsets.assign(ql.size() + 1, 0);
+  const std::size_t n_rec = ql.size() / rules.probes_per_record;
+  r.offsets.assign(n_rec + 1, 0);
   if (tl.empty() || ql.empty()) return r;
   auto check = [](int rc) {
     if (rc != BCU_OK) throw binary::VcfReaderError(std::string("libbinary_cuda: ") + bcu_last_error());
   };
   bcu_index* ix = nullptr;
   check(bcu_index_build(device, tl.size(), tg.data(), tl.data(), th.data(), &ix));
-  std::uint64_t total = 0, cap = 4 * ql.size() + 1024;
+  std::uint64_t total = 0, cap = 4 * n_rec + 1024;
   for (int attempt = 0; attempt < 2; ++attempt) {
     r.targets.resize(cap);
-    int rc = filter ? bcu_join_filtered(ix, filter, ql.size(), qg.data(), ql.data(), qh.data(),
-                                        qstrand ? qstrand->data() : nullptr, r.offsets.data(), cap, nullptr,
-                                        r.targets.data(), &total)
-                    : bcu_join(ix, ql.size(), qg.data(), ql.data(), qh.data(), r.offsets.data(), cap, nullptr,
-                               r.targets.data(), &total);
+    int rc = bcu_sv2nl_join(ix, filter, &rules, n_rec, qg.data(), ql.data(), qh.data(),
+                            qstrand ? qstrand->data() : nullptr, r.offsets.data(), cap, r.targets.data(), &total);
     if (rc == BCU_E_CAPACITY) { cap = total; continue; }
     if (rc != BCU_OK) { bcu_index_free(ix); check(rc); }
     break;
@@ -194,35 +180,33 @@ struct Lines {  // newline-terminated data lines of one output file, in one buff
 struct Sv2nlOutput { Lines dup, inv, tra; };
 
 namespace detail {
-// the common tail of the three map_impl loops: post-filter, duplicate-key rule, formatting
-template <class Check>
-Lines emit_lines(const Names& names, const std::vector<Rec>& nl_orig, const std::vector<Rec>& nl_valid,
-                 const std::vector<Rec>& sv_recs, const JoinResult& jr, Check&& check) {
+// the tail of the three map_impl loops: formatting (the pairs are the ones to write)
+inline Lines emit_lines(const Names& names, const std::vector<Rec>& nl_orig, const std::vector<Rec>& sv_recs,
+                        const JoinResult& jr) {
   Lines lines;
-  std::unordered_set<MapKey, MapKeyHash> written;  // SV2NL_USE_CACHE: keys of NL records already written
-  written.reserve(nl_orig.size() / 4 + 16);
-  std::vector<std::uint32_t> kept;
   std::string left;
   for (std::size_t q = 0; q < nl_orig.size(); ++q) {
-    if (jr.offsets[q] == jr.offsets[q + 1]) continue;  // no raw overlap: nothing can be kept or cached
-    const MapKey key = map_key(nl_orig[q]);
-    if (written.count(key)) continue;
-    kept.clear();
-    for (std::uint64_t k = jr.offsets[q]; k < jr.offsets[q + 1]; ++k)
-      if (check(nl_valid[q], sv_recs[jr.targets[k]])) kept.push_back(jr.targets[k]);
-    if (kept.empty()) continue;
-    written.insert(key);
+    if (jr.offsets[q] == jr.offsets[q + 1]) continue;
     left.clear();
     append_keys(left, nl_orig[q], names);
-    for (auto t : kept) {
+    for (std::uint64_t k = jr.offsets[q]; k < jr.offsets[q + 1]; ++k) {
       lines.text += left;
       lines.text += '\t';
-      append_keys(lines.text, sv_recs[t], names);
+      append_keys(lines.text, sv_recs[jr.targets[k]], names);
       lines.text += '\n';
       ++lines.count;
     }
   }
   return lines;
+}
+inline std::vector<std::uint32_t> key_words(const std::vector<Rec>& nl_orig) {  // format_map_key, four words each
+  std::vector<std::uint32_t> w;
+  w.reserve(4 * nl_orig.size());
+  for (auto const& r : nl_orig) {
+    const MapKey k = map_key(r);
+    w.insert(w.end(), {k.a, k.b, k.c, k.d});
+  }
+  return w;
 }
 }  // namespace detail
 
@@ -272,25 +256,20 @@ inline Sv2nlOutput map_sv2nl(const VcfTable& nl, const VcfTable& sv, const Optio
         qg.push_back(nl_valid.back().chrom); ql.push_back(nl_valid.back().pos); qh.push_back(nl_valid.back().svend);
         qstrand.push_back((std::uint8_t)((nl_valid.back().strand1 ? 1 : 0) | (nl_valid.back().strand2 ? 2 : 0)));
       }
-    // check_condition runs on the device (bcu_join_filtered); the host lambdas below re-check the few
-    // surviving pairs, which costs nothing and keeps one definition of the rules next to their citation
+    // check_condition (mapper.cpp:50-79) is fused into the join kernels, the duplicate-key rule follows on the device
     const bcu_filter filter{kind.inv ? (std::uint32_t)BCU_FILTER_SV2NL_INV : (std::uint32_t)BCU_FILTER_SV2NL_DUP,
                             opt.diff, opt.use_strand ? 1u : 0u, 0u};
+    const std::vector<std::uint32_t> keys = detail::key_words(nl_orig);
+    bcu_sv2nl_rules rules{};
+    rules.probes_per_record = 1;
+    rules.diff = opt.diff;
+    rules.dedup = 1;
+    rules.rec_key = keys.data();
     lap(kind.inv ? "inv: select records" : "dup: select records");
-    JoinResult jr = gpu_join(opt.device, tg, tl, th, qg, ql, qh, &filter, &qstrand);
-    lap(kind.inv ? "inv: index + join" : "dup: index + join");
-    auto check_dup = [&](const Rec& n, const Rec& s) {  // mapper.cpp:50-55
-      return is_contained(s, n) && distance_less(n, s, opt.diff);
-    };
-    auto check_inv = [&](const Rec& n, const Rec& s) {  // mapper.cpp:57-79
-      if (is_contained(s, n) || is_contained(n, s) || !distance_less(n, s, opt.diff)) return false;
-      if (!opt.use_strand) return true;
-      if (n.pos <= s.pos) return n.strand1 && !n.strand2;
-      return !n.strand1 && n.strand2;
-    };
-    if (kind.inv) out.inv = detail::emit_lines(names, nl_orig, nl_valid, sv_recs, jr, check_inv);
-    else out.dup = detail::emit_lines(names, nl_orig, nl_valid, sv_recs, jr, check_dup);
-    lap(kind.inv ? "inv: dedup + format" : "dup: dedup + format");
+    JoinResult jr = gpu_join(opt.device, tg, tl, th, qg, ql, qh, rules, &filter, &qstrand);
+    lap(kind.inv ? "inv: index + join + rules" : "dup: index + join + rules");
+    (kind.inv ? out.inv : out.dup) = detail::emit_lines(names, nl_orig, sv_recs, jr);
+    lap(kind.inv ? "inv: format" : "dup: format");
   }
 
   // ---- TraMapper ----------------------------------------------------------------------------------
@@ -299,8 +278,8 @@ inline Sv2nlOutput map_sv2nl(const VcfTable& nl, const VcfTable& sv, const Optio
   // join on the selective conditions -- group = (ordered chromosome pair, bucket of the SECOND breakpoint,
   // buckets `diff` wide), target = the point p1, query = [p1 - diff, p1 + diff] in each of the three buckets
   // a partner's p2 can fall into -- and apply the exact rules (both breakpoints within diff, and the
-  // reference's raw-interval overlap, which can still reject a pair) on the host. The three probes of a
-  // record are consecutive queries, so its hits are one contiguous CSR range.
+  // reference's raw-interval overlap, which can still reject a pair) to the pairs on the device. The three
+  // probes of a record are consecutive queries, so its hits are one contiguous CSR range.
   {
     std::vector<Rec> sv_recs, nl_orig, nl_valid;
     std::vector<std::uint32_t> tg, tl, th, qg, ql, qh;
@@ -350,21 +329,29 @@ inline Sv2nlOutput map_sv2nl(const VcfTable& nl, const VcfTable& sv, const Optio
         qg[3 * q + 1] = qg[3 * q + 2] = kNoGroup;
       }
     }
+    // TraMapper::check_condition (mapper.cpp:144-156), the raw-interval overlap of the reference's tree and the
+    // duplicate-key rule: on the device, over the three probes of each record (bcu_sv2nl_rules)
+    std::vector<std::uint32_t> rec_p1, rec_p2, tgt_p1, tgt_p2, tgt_pos, tgt_end;
+    for (auto const& n : nl_valid) { auto b = ordered_breakpoints(n); rec_p1.push_back(b.p1); rec_p2.push_back(b.p2); }
+    for (auto const& t : sv_recs) {
+      auto b = ordered_breakpoints(t);
+      tgt_p1.push_back(b.p1); tgt_p2.push_back(b.p2); tgt_pos.push_back(t.pos); tgt_end.push_back(t.svend);
+    }
+    const std::vector<std::uint32_t> keys = detail::key_words(nl_orig);
+    bcu_sv2nl_rules rules{};
+    rules.probes_per_record = 3;
+    rules.tra = 1;
+    rules.diff = opt.diff;
+    rules.dedup = 1;
+    rules.rec_p1 = rec_p1.data(); rules.rec_p2 = rec_p2.data();
+    rules.tgt_p1 = tgt_p1.data(); rules.tgt_p2 = tgt_p2.data();
+    rules.tgt_pos = tgt_pos.data(); rules.tgt_end = tgt_end.data();
+    rules.rec_key = keys.data();
     lap("tra: select records");
-    JoinResult probes = gpu_join(opt.device, tg, tl, th, qg, ql, qh);
-    JoinResult jr;  // per record: the three probes' ranges are adjacent
-    jr.offsets.resize(nl_orig.size() + 1);
-    for (std::size_t q = 0; q <= nl_orig.size(); ++q) jr.offsets[q] = probes.offsets[3 * q];
-    jr.targets = std::move(probes.targets);
-    lap("tra: index + join");
-    auto check_tra = [&](const Rec& n, const Rec& s) {
-      auto a = ordered_breakpoints(n), b = ordered_breakpoints(s);
-      if (!(a.c1 == b.c1 && a.c2 == b.c2)) return false;
-      if (!(absdiff(a.p1, b.p1) <= opt.diff && absdiff(a.p2, b.p2) <= opt.diff)) return false;
-      return n.pos <= s.svend && s.pos <= n.svend;  // the reference's find_overlaps on the raw intervals
-    };
-    out.tra = detail::emit_lines(names, nl_orig, nl_valid, sv_recs, jr, check_tra);
-    lap("tra: dedup + format");
+    JoinResult jr = gpu_join(opt.device, tg, tl, th, qg, ql, qh, rules);
+    lap("tra: index + join + rules");
+    out.tra = detail::emit_lines(names, nl_orig, sv_recs, jr);
+    lap("tra: format");
   }
   return out;
 }

@@ -47,6 +47,13 @@ for k, kw in enumerate(shapes):
             assert np.array_equal(off2, want_off) and np.array_equal(canonical(off2, ht2)[1], want_tid)
             assert np.array_equal(ix.any(c["ql"], c["qh"], c["qg"]), np.diff(want_off) > 0)
             g2 = ix.join_filtered(c["ql"], c["qh"], c["qg"], kind=2, diff=500, use_strand=False)
+            # the rules kernels (sv2nl_rules.cu): TRA columns indexed by record / target id, keys, three probes
+            n3 = c["ql"].size // 3
+            tra = dict(rec_p1=c["ql"][:n3], rec_p2=c["qh"][:n3], tgt_p1=c["tl"], tgt_p2=c["th"], tgt_pos=c["tl"], tgt_end=c["th"])
+            key = np.stack([c["ql"][:n3] % 7] * 4, axis=1)
+            qg3 = None if c["qg"] is None else c["qg"][:3 * n3]
+            if n3:
+                ix.sv2nl_join(c["ql"][:3 * n3], c["qh"][:3 * n3], qg3, diff=1000, probes_per_record=3, tra=tra, rec_key=key)
         ix.close()
 print("BOUNDS_OK", len(shapes))
 """
