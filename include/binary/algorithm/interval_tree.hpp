@@ -185,19 +185,36 @@ namespace algorithm::tree {
     explicit IntervalTree(int device = 0) : device_{device} {}
     // moves leave the source empty but usable (it gets a mutex of its own again)
     IntervalTree(IntervalTree&& o) noexcept
-        : device_{o.device_}, items_{std::move(o.items_)}, index_{std::move(o.index_)}, mutex_{std::move(o.mutex_)} {
+        : device_{o.device_}, devices_{std::move(o.devices_)}, items_{std::move(o.items_)},
+          index_{std::move(o.index_)}, replicas_{std::move(o.replicas_)}, mutex_{std::move(o.mutex_)} {
       o.items_.clear();
+      o.replicas_.clear();
       o.mutex_ = std::make_unique<std::mutex>();
     }
     IntervalTree& operator=(IntervalTree&& o) noexcept {
       if (this != &o) {
         device_ = o.device_;
+        devices_ = std::move(o.devices_);
         items_ = std::move(o.items_);
         index_ = std::move(o.index_);
+        replicas_ = std::move(o.replicas_);
         o.items_.clear();
         o.index_.reset();
+        o.replicas_.clear();
       }
       return *this;
+    }
+
+    /// Several GPUs for find_overlaps_batch: the index is replicated on every listed device and each batch is cut
+    /// into one contiguous query range per device (bcu_join_multi; the reference's counterpart is one thread-pool
+    /// task per chromosome over a shared tree, sv2nl mapper.hpp:238-246, mapper.cpp:136-140). The single-query
+    /// calls keep using the first device. An empty list returns to one device.
+    void use_devices(std::vector<int> devices) {
+      std::lock_guard lock{*mutex_};
+      devices_ = std::move(devices);
+      if (!devices_.empty()) device_ = devices_.front();
+      index_.reset();
+      replicas_.clear();
     }
     IntervalTree(IntervalTree const&) = delete;
     IntervalTree& operator=(IntervalTree const&) = delete;
@@ -213,6 +230,7 @@ namespace algorithm::tree {
     void insert_node(pointer node) {  // ownership transfer, as in the reference
       items_.push_back(std::move(node->interval));
       index_.reset();
+      replicas_.clear();
     }
 
     template <typename... Args>
@@ -220,6 +238,7 @@ namespace algorithm::tree {
     void insert_node(Args&&... args) {
       items_.push_back(std::move(NodeType(std::forward<Args>(args)...).interval));
       index_.reset();
+      replicas_.clear();
     }
 
     [[nodiscard]] auto size() const -> std::size_t { return items_.size(); }
@@ -322,6 +341,10 @@ namespace algorithm::tree {
         bcu_index* raw = nullptr;
         detail::check(bcu_index_build(device_, items_.size(), nullptr, low.data(), high.data(), &raw));
         index_.reset(raw);
+        for (std::size_t d = 1; d < devices_.size(); ++d) {  // replicas for bcu_join_multi
+          detail::check(bcu_index_build(devices_[d], items_.size(), nullptr, low.data(), high.data(), &raw));
+          replicas_.emplace_back(raw);
+        }
       }
       return index_.get();
     }
@@ -336,8 +359,16 @@ namespace algorithm::tree {
       std::uint64_t capacity = 4 * static_cast<std::uint64_t>(n) + 1024;
       for (int attempt = 0; attempt < 2; ++attempt) {
         res.target_ids.resize(capacity);
-        const int rc = bcu_join(ix, n, nullptr, ql, qh, res.offsets.data(), capacity, /*hit_query=*/nullptr,
-                                res.target_ids.data(), &total);
+        int rc;
+        if (devices_.empty()) {
+          rc = bcu_join(ix, n, nullptr, ql, qh, res.offsets.data(), capacity, /*hit_query=*/nullptr,
+                        res.target_ids.data(), &total);
+        } else {
+          std::vector<const bcu_index*> all{ix};
+          for (auto const& r : replicas_) all.push_back(r.get());
+          rc = bcu_join_multi(all.data(), static_cast<int>(all.size()), n, nullptr, ql, qh, res.offsets.data(),
+                              /*counts=*/nullptr, capacity, /*hit_query=*/nullptr, res.target_ids.data(), &total);
+        }
         if (rc == BCU_E_CAPACITY) {
           capacity = total;
           continue;
@@ -350,8 +381,10 @@ namespace algorithm::tree {
     }
 
     int device_{0};
+    std::vector<int> devices_{};  // use_devices(): non-empty = batches go through bcu_join_multi
     std::vector<interval_type> items_{};
     mutable std::unique_ptr<bcu_index, detail::IndexDeleter> index_{};
+    mutable std::vector<std::unique_ptr<bcu_index, detail::IndexDeleter>> replicas_{};
     mutable std::unique_ptr<std::mutex> mutex_{std::make_unique<std::mutex>()};
   };
 

@@ -137,6 +137,34 @@ int main(int argc, char** argv) {
     t.insert_node(200u, 300u);
     CHECK(t.find_overlaps(250u, 250u).size() == 1);
   }
+  {  // use_devices(): batches through bcu_join_multi (one device here when the box has one, every GPU otherwise)
+    int n_dev = 0;
+    CHECK(bcu_device_count(&n_dev) == BCU_OK && n_dev >= 1);
+    IntervalTree<IntIntervalNode> one{}, many{};
+    for (int i = 0; i < 20000; ++i) {
+      const int lo = (i * 7919) % 100003 - 50000, len = (i * 31) % 400;
+      one.insert_node(lo, lo + len);
+      many.insert_node(lo, lo + len);
+    }
+    std::vector<int> lo(50000), hi(50000);
+    for (int i = 0; i < 50000; ++i) { lo[i] = (int)(((long long)i * 104729) % 100003) - 50000; hi[i] = lo[i] + (i % 300); }
+    std::vector<int> devices;
+    for (int d = 0; d < n_dev; ++d) devices.push_back(d);
+    many.use_devices(devices);
+    auto a = one.find_overlaps_batch(std::span<const int>(lo), std::span<const int>(hi));
+    auto b = many.find_overlaps_batch(std::span<const int>(lo), std::span<const int>(hi));
+    CHECK(a.offsets == b.offsets && a.target_ids.size() == b.target_ids.size() && !a.target_ids.empty());
+    bool same = true;
+    for (std::size_t q = 0; q < lo.size() && same; ++q) {
+      std::multiset<std::uint32_t> x(a.hits(q).begin(), a.hits(q).end()), y(b.hits(q).begin(), b.hits(q).end());
+      same = x == y;
+    }
+    CHECK(same);
+    many.insert_node(0, 1);  // replicas are rebuilt after an insert
+    many.use_devices({0});
+    CHECK(many.find_overlaps_batch(std::span<const int>(lo), std::span<const int>(hi)).target_ids.size() > a.target_ids.size());
+    CHECK(many.find_overlaps(0, 0).size() == one.find_overlaps(0, 0).size() + 1);
+  }
   {  // empty tree
     IntervalTree<UIntIntervalNode> t{};
     CHECK(t.find_overlaps(1u, 2u).empty());
