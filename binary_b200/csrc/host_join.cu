@@ -122,6 +122,11 @@ static HostCtx* host_ctx(int device) {
   return ctx[device].get();
 }
 
+__global__ void counts_from_offsets_kernel(const uint64_t* __restrict__ off, uint64_t n, uint32_t* __restrict__ counts) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) counts[i] = (uint32_t)(off[i + 1] - off[i]);
+}
+
 void trim_host_ctx() {
   for (int d = 0; d < kMaxDevices; ++d) {
     HostCtx* c = host_ctx(d);
@@ -141,20 +146,24 @@ extern "C" int bcu_trim(void) {
   return BCU_OK;
 }
 
+// offsets (u64, n_q + 1) and/or counts (u32 hits per query, n_q: half the bytes over PCIe; plain joins only)
 static int join_host(const bcu_index* ix, const bcu_filter* filter, uint64_t n_q, const uint32_t* qgroup,
                      const uint32_t* qlow, const uint32_t* qhigh, const uint8_t* qstrand, uint64_t* offsets,
-                     uint64_t pair_capacity, uint32_t* hit_query, uint32_t* hit_target, uint64_t* total) {
+                     uint64_t pair_capacity, uint32_t* hit_query, uint32_t* hit_target, uint64_t* total,
+                     uint32_t* counts = nullptr) {
   if (!ix) { set_error("bcu_join: index is NULL"); return BCU_E_INVALID; }
   if (n_q && (!qlow || !qhigh)) { set_error("bcu_join: qlow/qhigh are NULL"); return BCU_E_INVALID; }
   if (n_q > 0xfffffffeull) { set_error("bcu_join: n_q exceeds 2^32-2"); return BCU_E_LIMIT; }
-  if (!offsets || !total) { set_error("bcu_join: offsets/total are NULL"); return BCU_E_INVALID; }
+  if ((!offsets && !counts) || !total) { set_error("bcu_join: offsets/total are NULL"); return BCU_E_INVALID; }
+  if (counts && qstrand) { set_error("bcu_join: per-query counts are not available with a strand filter"); return BCU_E_INVALID; }
   if (pair_capacity && !hit_target) {
     set_error("bcu_join: hit_target is NULL");
     return BCU_E_INVALID;
   }
   *total = 0;
   if (n_q == 0 || ix->n == 0) {
-    std::fill(offsets, offsets + n_q + 1, 0ull);
+    if (offsets) std::fill(offsets, offsets + n_q + 1, 0ull);
+    if (counts) std::fill(counts, counts + n_q, 0u);
     return BCU_OK;
   }
   DeviceGuard guard(ix->device);
@@ -184,6 +193,7 @@ static int join_host(const bcu_index* ix, const bcu_filter* filter, uint64_t n_q
   const uint64_t n_chunks = bounds.size() - 1;
   BCU_TRY(c->prepare(ix->device, n_q, pair_capacity, n_chunks, qgroup != nullptr, hit_query != nullptr,
                      qstrand != nullptr));
+  if (counts) BCU_TRY(c->grow(&c->d_qs, &c->cap_qs, n_q * 4));  // the strand column's buffer doubles as the u32 counts
 
   const bool trace = std::getenv("BCU_HOST_TRACE") != nullptr;  // dev aid: host-side timeline on stderr
   const auto t_begin = std::chrono::steady_clock::now();
@@ -203,6 +213,12 @@ static int join_host(const bcu_index* ix, const bcu_filter* filter, uint64_t n_q
                         qstrand ? c->d_qs + b : nullptr, c->h_totals_dev + i));
     // (no D2H copy of the total on s_run: it would queue behind s_out's large copies in the copy engine and
     // stall the next chunk's kernels; the kernel writes the total into mapped host memory instead)
+    if (counts) {  // the chunk's last offset is the next chunk's first: take it from the running total
+      BCU_CUDA(cudaMemcpyAsync(c->d_off + b + n, c->d_totals + i, 8, cudaMemcpyDeviceToDevice, c->s_run));
+      counts_from_offsets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->s_run>>>(
+          c->d_off + b, n, reinterpret_cast<uint32_t*>(c->d_qs) + b);
+      BCU_LAUNCHED();
+    }
     BCU_CUDA(cudaEventRecord(c->ev_run[i], c->s_run));
     if (trace) fprintf(stderr, "[bcu_join] chunk %llu (%llu queries) queued at %.0f us\n", (unsigned long long)i,
                        (unsigned long long)n, since());
@@ -217,7 +233,9 @@ static int join_host(const bcu_index* ix, const bcu_filter* filter, uint64_t n_q
                        since(), (unsigned long long)t);
     BCU_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_run[i], 0));
     const uint64_t n_off = n + (i + 1 == n_chunks ? 1 : 0);
-    BCU_CUDA(cudaMemcpyAsync(offsets + b, c->d_off + b, n_off * 8, cudaMemcpyDeviceToHost, c->s_out));
+    if (offsets) BCU_CUDA(cudaMemcpyAsync(offsets + b, c->d_off + b, n_off * 8, cudaMemcpyDeviceToHost, c->s_out));
+    if (counts)
+      BCU_CUDA(cudaMemcpyAsync(counts + b, reinterpret_cast<uint32_t*>(c->d_qs) + b, n * 4, cudaMemcpyDeviceToHost, c->s_out));
     const uint64_t upto = std::min(t, pair_capacity);
     if (upto > done_pairs) {
       if (hit_query)
@@ -276,11 +294,6 @@ extern "C" int bcu_join_filtered(const bcu_index* ix, const bcu_filter* filter, 
 #include <thread>
 
 namespace bcu {
-
-__global__ void counts_from_offsets_kernel(const uint64_t* __restrict__ off, uint64_t n, uint32_t* __restrict__ counts) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) counts[i] = (uint32_t)(off[i + 1] - off[i]);
-}
 
 class DeviceWorker {  // a thread that runs one job at a time on one device
  public:
@@ -438,6 +451,9 @@ extern "C" int bcu_join_multi(const bcu_index* const* indexes, int n_dev, uint64
       if (indexes[e]->device == indexes[d]->device) { set_error("bcu_join_multi: two indexes on device %d", indexes[d]->device); return BCU_E_INVALID; }
   }
   *total = 0;
+  if (n_dev == 1)  // no range needs another's total: the full-duplex chunk pipeline of bcu_join, with the counts option
+    return join_host(indexes[0], nullptr, n_q, qgroup, qlow, qhigh, nullptr, offsets, pair_capacity, hit_query, hit_target,
+                     total, counts);
   std::vector<MultiRange> ranges(n_dev);
   std::vector<DeviceWorker*> workers(n_dev);
   const uint64_t base_n = n_q / n_dev, extra = n_q % n_dev;  // binary_b200.sharding.shard_range

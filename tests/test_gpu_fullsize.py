@@ -47,6 +47,14 @@ def test_host_pipeline_many_chunks_vs_flat_oracle(port_oracle):
     off2, hq2, ht2 = ix.join(ql, qh, qg, pair_capacity=want_total, want_query_ids=False)
     assert hq2 is None and np.array_equal(off2, off)
     assert port_oracle.pair_hash(_qid_column(off2), ht2) == want_hash
+    # u32 counts instead of u64 offsets (bcu_join_multi on one device = the same chunk pipeline): what bench.py's
+    # e2e leg calls since round 2
+    from binary_b200 import join_multi
+    cnt3, hq3, ht3 = join_multi([ix], ql, qh, qg, pair_capacity=want_total, want_query_ids=False, counts32=True)
+    assert hq3 is None and cnt3.dtype == np.uint32 and np.array_equal(cnt3, want_counts)
+    assert port_oracle.pair_hash(_qid_column(off), ht3) == want_hash
+    cnt4, hq4, ht4 = join_multi([ix], ql[:4097], qh[:4097], qg[:4097], counts32=True)      # with the query column
+    assert np.array_equal(cnt4, want_counts[:4097]) and np.array_equal(hq4, _qid_column(off[:4098]))
     ix.close()
 
 
