@@ -21,7 +21,7 @@ of pairs); the device index is (re)built lazily on the first query after an inse
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Tuple
+from typing import Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -280,8 +280,12 @@ def join_multi(indexes, qlow, qhigh, qgroup=None, pair_capacity: Optional[int] =
 class IntervalTree:
     """Drop-in for the reference ``IntervalTree<IntervalNode<UIntInterval>>`` with a batched query."""
 
-    def __init__(self, device: int = 0):
-        self.device = device
+    def __init__(self, device: int = 0, devices: Optional[Sequence[int]] = None):
+        """``devices``: several GPUs for ``find_overlaps_batch`` -- the index is replicated on each and every batch is
+        cut into one contiguous query range per device (``bcu_join_multi``); single queries use the first."""
+        self.devices = list(devices) if devices else None
+        self.device = self.devices[0] if self.devices else device
+        self._replicas: list = []
         self._low: list = []
         self._high: list = []
         self._group: list = []
@@ -303,6 +307,7 @@ class IntervalTree:
         self._high.append(hi)
         self._group.append(g)
         self._index = None
+        self._replicas = []
 
     def size(self) -> int:
         return int(sum(a.size for a in self._low))
@@ -316,11 +321,16 @@ class IntervalTree:
             self._arrays = (cat(self._low), cat(self._high), cat(self._group))
             self._low, self._high, self._group = [self._arrays[0]], [self._arrays[1]], [self._arrays[2]]
             self._index = DeviceIndex.build(*self._arrays, device=self.device)
+            self._replicas = [DeviceIndex.build(*self._arrays, device=d) for d in (self.devices or [])[1:]]
         return self._index
 
     def find_overlaps_batch(self, qlow, qhigh, qgroup=None):
         """CSR ``(offsets u64[n_q+1], target_ids u32[total])``; ids are insertion ordinals."""
-        offsets, _, target = self._ensure().join(qlow, qhigh, qgroup, want_query_ids=False)
+        ix = self._ensure()
+        if self.devices:
+            offsets, _, target = join_multi([ix] + self._replicas, qlow, qhigh, qgroup, want_query_ids=False)
+        else:
+            offsets, _, target = ix.join(qlow, qhigh, qgroup, want_query_ids=False)
         return offsets, target
 
     def find_overlaps(self, low: int, high: int, group: int = 0):

@@ -46,3 +46,20 @@ def test_join_multi_equals_oracle(port_oracle, n_dev, monkeypatch):
     assert np.array_equal(off1, want_off[:2]) and np.array_equal(np.sort(ht1), want_tid[:int(want_off[1])])
     for ix in indexes:
         ix.close()
+
+
+def test_python_drop_in_over_every_visible_gpu(port_oracle):
+    """``IntervalTree(devices=[...])``: batches through bcu_join_multi over replicas, single queries on the first."""
+    from binary_b200 import IntervalTree
+    c = random_case(91, n_t=30000, n_q=40000, n_groups=3, span=2_000_000, max_len=3000)
+    f = port_oracle.build(c["tl"], c["th"], c["tg"])
+    want_off, want_tid = f.query_sorted_pairs(c["ql"], c["qh"], c["qg"], threads=4)
+    t = IntervalTree(devices=list(range(_device_count())))
+    t.insert_node(c["tl"], c["th"], c["tg"])
+    off, tid = t.find_overlaps_batch(c["ql"], c["qh"], c["qg"])
+    assert np.array_equal(off, want_off) and np.array_equal(canonical(off, tid)[1], want_tid)
+    q = int(np.argmax(np.diff(want_off)))
+    hits = t.find_overlaps(int(c["ql"][q]), int(c["qh"][q]), int(c["qg"][q]))
+    assert sorted(h[2] for h in hits) == sorted(want_tid[int(want_off[q]):int(want_off[q + 1])].tolist())
+    t.insert_node(5, 6, 0)                                      # replicas are rebuilt after an insert
+    assert len(t.find_overlaps(5, 5, 0)) >= 1 and t.size() == 30001
