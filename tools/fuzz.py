@@ -1,5 +1,6 @@
 """Randomised parity fuzz on the GPU: many small cases of random shape through every entry point of the C ABI
-against the oracle tree walk. usage: python tools/fuzz.py [n_cases] [first_seed]"""
+against the oracle tree walk. Every third case forces the stab lists of the long-range emit (BCU_LONG_LISTS=1), every
+third the binned path with a random tile size (device-buffer join). usage: python tools/fuzz.py [n_cases] [first_seed]"""
 import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -7,6 +8,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle
 from binary_b200 import DeviceIndex
 from cases import canonical, random_case
+from test_gpu_binned import dev_join
 
 n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
@@ -24,9 +26,18 @@ for s in range(seed0, seed0 + n_cases):
         idx = r.choice(c["ql"].size, max(1, c["ql"].size // 10), replace=False)
         c["ql"][idx], c["qh"][idx] = c["qh"][idx].copy(), c["ql"][idx].copy()
     want_off, want_tid = port.build(c["tl"], c["th"], c["tg"]).query_sorted_pairs(c["ql"], c["qh"], c["qg"], threads=8)
+    variant = s % 3
+    for k in ("BCU_LONG_LISTS", "BCU_BINNED", "BCU_BIN_ROWS", "BCU_BINNED_COVER"):
+        os.environ.pop(k, None)
+    if variant >= 1:
+        os.environ["BCU_LONG_LISTS"] = "1"
+    if variant == 2:
+        os.environ.update(BCU_BINNED="1", BCU_BIN_ROWS=str(int(r.choice([64, 256, 1024, 8192]))), BCU_BINNED_COVER="1e9")
     ix = DeviceIndex.build(c["tl"], c["th"], c["tg"])
     off, hq, ht = ix.join(c["ql"], c["qh"], c["qg"])
     ok = np.array_equal(off, want_off) and np.array_equal(canonical(off, ht)[1], want_tid)
+    offd, hqd, htd = dev_join(ix, c["ql"], c["qh"], c["qg"])   # device buffers: the binned path when the index has tiles
+    ok = ok and np.array_equal(offd, want_off) and np.array_equal(canonical(offd, htd)[1], want_tid)
     off2 = ix.count(c["ql"], c["qh"], c["qg"])
     hq2, ht2 = ix.scatter(c["ql"], c["qh"], off2, c["qg"])
     ok = ok and np.array_equal(off2, want_off) and np.array_equal(canonical(off2, ht2)[1], want_tid) and np.array_equal(hq, hq2)
