@@ -41,6 +41,8 @@ def _load():
             getattr(lib, name).argtypes = [s, u, u, s, s, C.c_char_p, i]
         lib.sv2nl_ref_run.restype = i
         lib.sv2nl_ref_run.argtypes = [s, s, s, u, i, i]
+        lib.sv2nl_ref_run_some.restype = i
+        lib.sv2nl_ref_run_some.argtypes = [s, s, s, u, i, i, i]
         _lib = lib
     return _lib
 
@@ -82,9 +84,11 @@ def format_keys(r) -> str:
 
 
 def run(nl_path: str, sv_path: str, out_prefix: str, diff: int = 1_000_000, threads: int = 4,
-        use_strand: bool = True) -> Dict[str, List[str]]:
-    """Runs the reference's three mappers; returns the DATA lines of <prefix>.dup/.inv/.tra (header checked)."""
-    rc = _load().sv2nl_ref_run(_b(nl_path), _b(sv_path), _b(out_prefix), diff, threads, int(use_strand))
+        use_strand: bool = True, mappers=("dup", "inv", "tra")) -> Dict[str, List[str]]:
+    """Runs the reference's mappers (all three by default); returns the DATA lines of <prefix>.dup/.inv/.tra (header
+    checked; a mapper that was left out has none)."""
+    mask = sum(bit for name, bit in (("dup", 1), ("inv", 2), ("tra", 4)) if name in mappers)
+    rc = _load().sv2nl_ref_run_some(_b(nl_path), _b(sv_path), _b(out_prefix), diff, threads, int(use_strand), mask)
     if rc != 0:
         raise RuntimeError("reference sv2nl run failed")
     out = {}

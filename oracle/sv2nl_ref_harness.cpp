@@ -6,7 +6,7 @@
 //   /root/reference/library/include/binary/parser/vcf.hpp, library/source/utils.cpp
 // (compiled from where they lie by oracle/Makefile; nothing is copied into this repo) behind a C ABI:
 //
-//   sv2nl_ref_run           = what the reference's main.cpp `run()` does (main.cpp:47-84): DupMapper, InvMapper
+//   sv2nl_ref_run[_some]    = what the reference's main.cpp `run()` does (main.cpp:47-84): DupMapper, InvMapper
 //                             and TraMapper over one thread pool, outputs <prefix>.dup/.inv/.tra. main.cpp itself
 //                             needs cxxopts (absent from the image), so its ten lines of set-up are repeated here.
 //   sv2nl_ref_check         = {Dup,Inv,Tra}Mapper::check_condition (mapper.cpp:50-79,144-156) on two records
@@ -110,8 +110,11 @@ int sv2nl_ref_format_keys(const char* chrom, std::uint32_t pos, std::uint32_t sv
 }
 
 // The reference tool's run(): three mappers, one pool (destroyed -- i.e. drained -- before the writers close).
-int sv2nl_ref_run(const char* nl, const char* sv, const char* out_prefix, std::uint32_t diff, int threads,
-                  int use_strand) {
+// mappers: bit 0 DupMapper, bit 1 InvMapper, bit 2 TraMapper (a mapper left out still writes its header line). The
+// reference's TraMapper visits a large fraction of ALL BND records per NL record (one tree over raw [POS, POS2]
+// intervals, mapper.cpp:103): at config E's full size that is ~3e11 pair visits, so the full-size comparison leaves it out.
+int sv2nl_ref_run_some(const char* nl, const char* sv, const char* out_prefix, std::uint32_t diff, int threads,
+                       int use_strand, int mappers) {
   try {
     const std::string dup_out = std::string(out_prefix) + ".dup", inv_out = std::string(out_prefix) + ".inv",
                       tra_out = std::string(out_prefix) + ".tra";
@@ -120,9 +123,9 @@ int sv2nl_ref_run(const char* nl, const char* sv, const char* out_prefix, std::u
     auto tra = sv2nl::TraMapper(opts(nl, sv, tra_out, "TRA", "BND", diff, true));
     {
       auto pool = dp::thread_pool(threads > 0 ? (unsigned)threads : 4u);
-      dup.map(pool);
-      inv.map(pool);
-      tra.map(pool);
+      if (mappers & 1) dup.map(pool);
+      if (mappers & 2) inv.map(pool);
+      if (mappers & 4) tra.map(pool);
     }
     tra.close_writer();
     inv.close_writer();
@@ -132,6 +135,10 @@ int sv2nl_ref_run(const char* nl, const char* sv, const char* out_prefix, std::u
     std::fprintf(stderr, "sv2nl_ref_run: %s\n", e.what());
     return -1;
   }
+}
+int sv2nl_ref_run(const char* nl, const char* sv, const char* out_prefix, std::uint32_t diff, int threads,
+                  int use_strand) {
+  return sv2nl_ref_run_some(nl, sv, out_prefix, diff, threads, use_strand, 7);
 }
 
 }  // extern "C"

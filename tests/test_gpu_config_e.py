@@ -5,8 +5,10 @@ line count and an order-independent hash of the lines of each of the three outpu
 define the order: its tasks interleave).
 
 Default size 60 k SV x 300 k NL records so that the suite stays within minutes (the reference tool re-parses both
-files in every chromosome task, mapper.hpp:196-197); BCU_TEST_FULL_E=1 runs the configuration's own 1 M x 5 M
-(profiles/r02_config_e.txt holds that run)."""
+files in every chromosome task, mapper.hpp:196-197). BCU_TEST_FULL_E=1 runs the configuration's own 1 M x 5 M for the
+DUP and INV files (profiles/r02_config_e.txt holds that run); the reference's TraMapper is left out at that size: it
+joins on the raw [POS, POS2] intervals of ALL BND records (mapper.cpp:103), so an NL record visits a large fraction
+of them -- 1.25 M x 250 k = 3e11 pair visits, hours on the host (the first attempt at it was stopped after 35 min)."""
 import os
 import subprocess
 import time
@@ -34,17 +36,21 @@ def test_config_e_full_set_count_and_hash(tmp_path):
     t_tool = time.time() - t0
     assert r.returncode == 0, r.stderr
     t0 = time.time()
-    want = sv2nl_ref.run(nl_path, sv_path, str(tmp_path / "ref"), threads=os.cpu_count() or 4)
+    exts = ("dup", "inv") if full else ("dup", "inv", "tra")
+    want = sv2nl_ref.run(nl_path, sv_path, str(tmp_path / "ref"), threads=os.cpu_count() or 4, mappers=exts)
     t_ref = time.time() - t0
-    report = [f"config E {n_sv} SV x {n_nl} NL records: tool {t_tool:.2f} s, reference tool {t_ref:.2f} s "
-              f"({os.cpu_count()} host threads)"]
+    report = [f"config E {n_sv} SV x {n_nl} NL records: tool (all three mappers) {t_tool:.2f} s, reference tool "
+              f"({'+'.join(exts)}) {t_ref:.2f} s ({os.cpu_count()} host threads)"]
     for ext in ("dup", "inv", "tra"):
         got = open(f"{out}.{ext}").read().splitlines()
         assert got[0] == "chrom\tpos\tend\tsvtype\tchrom\tpos\tend\tsvtype"
+        if ext not in exts:
+            report.append(f"  .{ext}: {len(got) - 1} lines (not compared at this size, see the module docstring)")
+            continue
         g, w = line_set_digest(got[1:]), line_set_digest(want[ext])
         report.append(f"  .{ext}: {g[0]} lines, hash {g[1]:016x} (reference: {w[0]} lines, {w[1]:016x})")
         assert g == w, ext
-    assert sum(len(want[e]) for e in want) > 0
+    assert sum(len(want[e]) for e in exts) > 0
     print("\n".join(report))
     if os.environ.get("BCU_REPORT_DIR"):
         with open(os.path.join(os.environ["BCU_REPORT_DIR"], "config_e.txt"), "w") as fh:
