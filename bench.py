@@ -450,6 +450,9 @@ def run_ours(args):
         hits_all = j.n_hits
     ms_per_step = dev_ms_total / args.steps
     value = j.n_total / (ms_per_step * 1e-3)
+    if e2e is not None:  # whole-job bytes (all ranks), like `value`
+        e2e["h2d_bytes_per_step"] = 12 * j.n_total
+        e2e["d2h_bytes_per_step"] = 4 * j.n_total + 4 * hits_all
 
     line = None
     if rank == 0:
