@@ -610,17 +610,46 @@ __global__ void __launch_bounds__(kPlaceThreads, 2) bin_place_kernel(const Binne
   const uint32_t tile = s_tile;
   const uint32_t K = a.n_bins;
   const uint16_t* trun = a.trun + (uint64_t)tile * (K + 2);
-  const uint32_t n_live = trun[K], n_here = trun[K + 1];  // slots with a bin / queries of the tile
   const uint64_t q0 = (uint64_t)tile * kTileQ;
   const uint2* const sres = a.sres + q0;
-
-  for (uint32_t s = tid; s < (uint32_t)kTileQ; s += kPlaceThreads) {
-    s_loc[s] = s < n_here ? a.bloc[q0 + s] : (uint16_t)0;
+  // Everything the tile needs from global memory is requested at once (one round trip instead of three dependent
+  // ones), and the tile's hit total is published for the look-back of the later tiles as soon as the counts are
+  // there -- before the scatter and the scan: in the round-2 profile a third of this phase was the look-back warp
+  // spinning on predecessors that had not published yet (and the other warps waiting for it at the barrier).
+  const uint32_t n_here = (uint32_t)min((uint64_t)kTileQ, (uint64_t)a.n_q - q0);  // queries of the tile (== trun[K + 1])
+  const uint32_t n_live_ld = trun[K];                                             // slots with a bin
+  uint32_t cnt_r[kPlaceQPT], loc_r[kPlaceQPT];
+#pragma unroll
+  for (int k = 0; k < kPlaceQPT; ++k) {
+    const uint32_t s = (uint32_t)(k * kPlaceThreads + tid);
+    loc_r[k] = s < n_here ? (uint32_t)a.bloc[q0 + s] : 0u;
+    cnt_r[k] = s < n_here ? sres[s].y : 0u;  // (slots without a bin hold no result: masked below)
     s_off[s] = 0;
   }
-  __syncthreads();
-  BCU_DEV_ASSERT(n_live <= n_here && n_here <= (uint32_t)kTileQ);
-  for (uint32_t s = tid; s < n_live; s += kPlaceThreads) s_off[s_loc[s]] = sres[s].y;  // counts by query position
+  const uint32_t n_live = n_live_ld;
+  BCU_DEV_ASSERT(n_live <= n_here && n_here <= (uint32_t)kTileQ && n_here == trun[K + 1]);
+  uint64_t early = 0;
+#pragma unroll
+  for (int k = 0; k < kPlaceQPT; ++k) {
+    if ((uint32_t)(k * kPlaceThreads + tid) >= n_live) cnt_r[k] = 0;
+    early += cnt_r[k];
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) early += shfl_down_u64(early, o);
+  if (lane == 0) s_scan[warp] = early;
+  __syncthreads();  // (also: s_off is zeroed)
+  if (warp == 0) {
+    uint64_t v = lane < kPlaceThreads / 32 ? s_scan[lane] : 0ull;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += shfl_down_u64(v, o);
+    if (lane == 0) reinterpret_cast<volatile uint64_t*>(a.status)[tile] = (tile == 0 ? kStInclusive : kStAggregate) | v;
+  }
+#pragma unroll
+  for (int k = 0; k < kPlaceQPT; ++k) {  // counts by query position
+    const uint32_t s = (uint32_t)(k * kPlaceThreads + tid);
+    s_loc[s] = (uint16_t)loc_r[k];
+    if (s < n_live) s_off[loc_r[k]] = cnt_r[k];
+  }
   __syncthreads();
   // exclusive scan over the tile's 4096 counts (kPlaceQPT consecutive entries per thread)
   uint32_t c[kPlaceQPT];
