@@ -12,6 +12,8 @@
 //   size(), empty()                                     rb_tree.hpp:126-129
 // plus the NEW batched entry point the sv2nl loop (standalone/sv2nl/include/mapper.hpp:207-218) needs:
 //   find_overlaps_batch(span<const interval_type>) -> {offsets, target ids}
+// and use_devices({0, 1, ...}): batches split over several GPUs (bcu_join_multi; the counterpart of the reference's
+// one-task-per-chromosome pool over a shared tree, mapper.hpp:238-246, mapper.cpp:136-140).
 //
 // What differs, on purpose:
 //   * there is no pointer tree: intervals (with whatever payload the Interval subclass carries) stay in a
